@@ -1,0 +1,182 @@
+// Operator A: PML tables, CSR assembly and the matrix-free 5-point stencil matvec.
+//
+// Replaces the numba assembly loops get_A_diag_block_coeffs / get_upper_A_block / get_lower_A_block and
+// the scipy glue of build_A_matrix (/root/reference/code.py:71-219).  The coefficient of grid point (i, j)
+// towards its neighbours is separable,
+//     c1 = s1((i-.5)h)/(h^2 s2(jh))   c2 = s1((i+.5)h)/(h^2 s2(jh))
+//     c3 = s2((j-.5)h)/(h^2 s1(ih))   c4 = s2((j+.5)h)/(h^2 s1(ih))
+//     c5 = omega^2/(s1 s2 c^2) - (c1+c2+c3+c4),
+// so the stretching factors are evaluated once per grid line (2n+3 half-grid points per axis, kernel
+// hp_tables_kernel) and the per-point work is a handful of complex multiplies: both kernels below are
+// HBM-bound (CSR: 104 B written per row; matvec: 40 B per grid point).
+#include "hp_internal.cuh"
+
+__global__ void hp_tables_kernel(int n, HpPml p, cplx* s1t, cplx* is1t, cplx* s2t, cplx* is2t) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= 2 * n + 2) hp_table_entry(t, p, s1t + t, is1t + t, s2t + t, is2t + t);
+}
+
+// kappa[(j-1) n + (i-1)] = 1/c_mat[i-1][j-1]^2 : the reference's transposed velocity lookup (code.py:108)
+// turned into a grid-aligned array so that the stencil kernels read it coalesced.  32x32 smem transpose.
+__global__ void hp_kappa_kernel(int n, const double* __restrict__ c_mat, double* __restrict__ kappa) {
+    __shared__ double tile[32][33];
+    int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int i = i0 + r, j = j0 + threadIdx.x;        // read c_mat[i][j], j fastest
+        if (i < n && j < n) tile[r][threadIdx.x] = c_mat[(size_t)i * (n + 2) + j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int j = j0 + r, i = i0 + threadIdx.x;        // write kappa[j][i], i fastest
+        if (i < n && j < n) {
+            double c = tile[threadIdx.x][r];
+            kappa[(size_t)j * n + i] = 1.0 / (c * c);
+        }
+    }
+}
+
+int hp_launch_tables(hp_solver* s, cudaStream_t st) {
+    int n = s->n, len = 2 * n + 3;
+    hp_tables_kernel<<<(len + 127) / 128, 128, 0, st>>>(n, s->pml, s->s1t, s->is1t, s->s2t, s->is2t);
+    dim3 blk(32, 8), grd((n + 31) / 32, (n + 31) / 32);
+    hp_kappa_kernel<<<grd, blk, 0, st>>>(n, s->c_mat, s->kappa);
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+struct HpPointCoef { cplx c1, c2, c3, c4, c5; };
+
+__device__ __forceinline__ HpPointCoef hp_point_coef(int i, int j, int n, double ih2, cplx omega2,
+                                                     const cplx* __restrict__ s1t, const cplx* __restrict__ is1t,
+                                                     const cplx* __restrict__ s2t, const cplx* __restrict__ is2t,
+                                                     double kap) {
+    // i, j are 1-based grid indices
+    cplx is2c = is2t[2 * j], is1c = is1t[2 * i];
+    HpPointCoef c;
+    c.c1 = cscale(ih2, cmul(s1t[2 * i - 1], is2c));
+    c.c2 = cscale(ih2, cmul(s1t[2 * i + 1], is2c));
+    c.c3 = cscale(ih2, cmul(s2t[2 * j - 1], is1c));
+    c.c4 = cscale(ih2, cmul(s2t[2 * j + 1], is1c));
+    cplx t = cscale(kap, cmul(omega2, cmul(is1c, is2c)));
+    c.c5 = csub(t, cadd(cadd(c.c1, c.c2), cadd(c.c3, c.c4)));
+    return c;
+}
+
+// One thread per matrix row.  Row r = (j-1) n + (i-1) stores, in ascending column order, the couplings
+// to (i, j-1), (i-1, j), itself, (i+1, j), (i, j+1); neighbours outside the grid are dropped.  The row
+// offset has a closed form, so indptr needs no scan.
+__global__ void __launch_bounds__(256) hp_assemble_csr_kernel(int n, double ih2, cplx omega2,
+        const cplx* __restrict__ s1t, const cplx* __restrict__ is1t, const cplx* __restrict__ s2t,
+        const cplx* __restrict__ is2t, const double* __restrict__ kappa,
+        int32_t* __restrict__ indptr, int32_t* __restrict__ indices, cplx* __restrict__ data) {
+    int64_t N = (int64_t)n * n;
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    int j0 = (int)(r / n), i0 = (int)(r % n);
+    int64_t nn = n;
+    int64_t off = 5 * r - (r < nn ? r : nn) - (r > (nn - 1) * nn ? r - (nn - 1) * nn : 0)
+                  - (j0 + (i0 > 0 ? 1 : 0)) - j0;
+    HpPointCoef c = hp_point_coef(i0 + 1, j0 + 1, n, ih2, omega2, s1t, is1t, s2t, is2t, kappa[r]);
+    indptr[r] = (int32_t)off;
+    int64_t o = off;
+    if (j0 > 0)     { indices[o] = (int32_t)(r - n); data[o] = c.c3; ++o; }
+    if (i0 > 0)     { indices[o] = (int32_t)(r - 1); data[o] = c.c1; ++o; }
+                      indices[o] = (int32_t)r;       data[o] = c.c5; ++o;
+    if (i0 < n - 1) { indices[o] = (int32_t)(r + 1); data[o] = c.c2; ++o; }
+    if (j0 < n - 1) { indices[o] = (int32_t)(r + n); data[o] = c.c4; ++o; }
+    if (r == N - 1) indptr[N] = (int32_t)o;
+}
+
+// Matrix-free y = A x.  A CTA owns 128 consecutive x1 columns and marches over HP_SPMV_ROWS grid rows;
+// each thread keeps the x2 neighbours (south, centre, north) of its column in registers, takes the x1
+// neighbours from the adjacent lanes by shuffle (warp-edge lanes read them from L1/L2) and keeps the
+// x1-dependent factors in registers for the whole march.  Algorithmic traffic per grid point:
+// x 16 B read + y 16 B written + kappa 8 B read = 40 B.
+#define HP_SPMV_ROWS 16
+__global__ void __launch_bounds__(128) hp_stencil_matvec_kernel(int n, double ih2, cplx omega2,
+        const cplx* __restrict__ s1t, const cplx* __restrict__ is1t, const cplx* __restrict__ s2t,
+        const cplx* __restrict__ is2t, const double* __restrict__ kappa,
+        const cplx* __restrict__ x, cplx* __restrict__ y) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int j0 = blockIdx.y * HP_SPMV_ROWS;
+    const bool act = col < n;
+    const cplx zero = cmake(0.0, 0.0);
+    cplx aW = zero, aE = zero, dI = zero, wI = zero;
+    if (act) {
+        aW = cscale(ih2, s1t[2 * col + 1]);       // s1((i-.5)h)/h^2, i = col+1
+        aE = cscale(ih2, s1t[2 * col + 3]);       // s1((i+.5)h)/h^2
+        dI = is1t[2 * col + 2];                   // 1/s1(ih)
+        wI = cmul(omega2, dI);
+    }
+    cplx xS = (act && j0 > 0) ? x[(size_t)(j0 - 1) * n + col] : zero;
+    cplx xC = act ? x[(size_t)j0 * n + col] : zero;
+#pragma unroll 4
+    for (int r = 0; r < HP_SPMV_ROWS; ++r) {
+        const int j = j0 + r;                       // 0-based grid row, uniform over the CTA
+        if (j >= n) break;
+        const size_t base = (size_t)j * n;
+        cplx xN = (act && j + 1 < n) ? x[base + n + col] : zero;
+        double kap = act ? kappa[base + col] : 0.0;
+        cplx xW, xE;
+        xW.x = __shfl_up_sync(0xffffffffu, xC.x, 1);
+        xW.y = __shfl_up_sync(0xffffffffu, xC.y, 1);
+        xE.x = __shfl_down_sync(0xffffffffu, xC.x, 1);
+        xE.y = __shfl_down_sync(0xffffffffu, xC.y, 1);
+        if (lane == 0) xW = (act && col > 0) ? x[base + col - 1] : zero;
+        if (lane == 31) xE = (col + 1 < n) ? x[base + col + 1] : zero;
+        const cplx bJ = is2t[2 * j + 2];                       // 1/s2(jh)
+        const cplx gS = cscale(ih2, s2t[2 * j + 1]);            // s2((j-.5)h)/h^2
+        const cplx gN = cscale(ih2, s2t[2 * j + 3]);            // s2((j+.5)h)/h^2
+        // y = c5 xC + c1 xW + c2 xE + c3 xS + c4 xN with c5 = kappa omega^2 dI bJ - (c1+c2+c3+c4)
+        cplx t1 = cfma(aW, csub(xW, xC), cmul(aE, csub(xE, xC)));
+        cplx t2 = cfma(gS, csub(xS, xC), cmul(gN, csub(xN, xC)));
+        cplx acc = cmul(cscale(kap, cmul(wI, bJ)), xC);
+        acc = cfma(bJ, t1, acc);
+        acc = cfma(dI, t2, acc);
+        if (act) y[base + col] = acc;
+        xS = xC;
+        xC = xN;
+    }
+}
+
+__global__ void __launch_bounds__(256) hp_csr_matvec_kernel(int64_t nrows, const int32_t* __restrict__ indptr,
+        const int32_t* __restrict__ indices, const cplx* __restrict__ data, const cplx* __restrict__ x,
+        cplx* __restrict__ y) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    cplx acc = cmake(0.0, 0.0);
+    for (int32_t e = indptr[r]; e < indptr[r + 1]; ++e) acc = cfma(data[e], x[indices[e]], acc);
+    y[r] = acc;
+}
+
+extern "C" int64_t hp_csr_nnz(int n) { return 5 * (int64_t)n * n - 4 * (int64_t)n; }
+
+extern "C" int hp_assemble_csr(hp_solver* s, int32_t* indptr, int32_t* indices, double* data, void* stream) {
+    if (!s) { hp_set_error("hp_assemble_csr: null solver"); return 1; }
+    if (hp_csr_nnz(s->n) > 2147483647LL) { hp_set_error("hp_assemble_csr: nnz exceeds int32 indices"); return 1; }
+    int64_t N = (int64_t)s->n * s->n;
+    double ih2 = 1.0 / (s->pml.h * s->pml.h);
+    hp_assemble_csr_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        s->n, ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa, indptr, indices, (cplx*)data);
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hp_stencil_matvec(hp_solver* s, const double* x, double* y, void* stream) {
+    if (!s) { hp_set_error("hp_stencil_matvec: null solver"); return 1; }
+    double ih2 = 1.0 / (s->pml.h * s->pml.h);
+    dim3 grd((s->n + 127) / 128, (s->n + HP_SPMV_ROWS - 1) / HP_SPMV_ROWS);
+    hp_stencil_matvec_kernel<<<grd, 128, 0, (cudaStream_t)stream>>>(
+        s->n, ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa, (const cplx*)x, (cplx*)y);
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hp_csr_matvec(int64_t nrows, const int32_t* indptr, const int32_t* indices, const double* data,
+                             const double* x, double* y, void* stream) {
+    hp_csr_matvec_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        nrows, indptr, indices, (const cplx*)data, (const cplx*)x, (cplx*)y);
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,181 @@
+// Krylov vector kernels: the numpy calls of scipy's gmres inner loop (np.vdot, np.linalg.norm, w -= h*v,
+// x += y @ V; scipy/sparse/linalg/_isolve/iterative.py as called from /root/reference/code.py:516).
+//
+// Reductions are single-launch and deterministic: every CTA reduces a fixed slice with warp shuffles and
+// writes one partial; the CTA that draws the last ticket sums the partials in index order.  All calls of
+// one process are expected on one stream (they share the partial buffer).
+#include "hp_internal.cuh"
+
+#define HP_RED_THREADS 256
+#define HP_RED_MAX_CTAS 1184   // 8 per SM on a 148-SM part
+
+static cplx* g_partials = nullptr;
+static unsigned int* g_ticket = nullptr;
+
+static int hp_red_scratch() {
+    if (!g_partials) {
+        HP_CUDA(cudaMalloc(&g_partials, sizeof(cplx) * HP_RED_MAX_CTAS));
+        HP_CUDA(cudaMalloc(&g_ticket, sizeof(unsigned int)));
+        HP_CUDA(cudaMemset(g_ticket, 0, sizeof(unsigned int)));
+    }
+    return 0;
+}
+
+__device__ __forceinline__ cplx hp_warp_sum(cplx v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    return v;
+}
+
+// MODE 0: out = sum conj(x) y ; MODE 1: out = (sqrt(sum |x|^2), 0)
+template <int MODE>
+__global__ void __launch_bounds__(HP_RED_THREADS) hp_reduce_kernel(int64_t n, const cplx* __restrict__ x,
+        const cplx* __restrict__ y, cplx* __restrict__ partials, unsigned int* ticket, cplx* __restrict__ out) {
+    __shared__ cplx wsum[HP_RED_THREADS / 32];
+    __shared__ bool last;
+    cplx acc = cmake(0.0, 0.0);
+    const int64_t stride = (int64_t)gridDim.x * HP_RED_THREADS;
+    for (int64_t e = (int64_t)blockIdx.x * HP_RED_THREADS + threadIdx.x; e < n; e += stride) {
+        cplx a = x[e];
+        if (MODE == 0) {
+            cplx b = y[e];
+            acc.x = fma(a.x, b.x, fma(a.y, b.y, acc.x));
+            acc.y = fma(a.x, b.y, fma(-a.y, b.x, acc.y));
+        } else {
+            acc.x = fma(a.x, a.x, fma(a.y, a.y, acc.x));
+        }
+    }
+    acc = hp_warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cplx t = wsum[0];
+        for (int w = 1; w < HP_RED_THREADS / 32; ++w) t = cadd(t, wsum[w]);
+        partials[blockIdx.x] = t;
+        __threadfence();
+        unsigned int k = atomicAdd(ticket, 1u);
+        last = (k == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 32) {
+        __threadfence();
+        cplx t = cmake(0.0, 0.0);
+        const volatile double* pv = (const volatile double*)partials;   // written by other CTAs: bypass L1
+        for (int c = threadIdx.x; c < (int)gridDim.x; c += 32) t = cadd(t, cmake(pv[2 * c], pv[2 * c + 1]));
+        t = hp_warp_sum(t);
+        if (threadIdx.x == 0) {
+            if (MODE == 1) t = cmake(sqrt(t.x), 0.0);
+            *out = t;
+            *ticket = 0u;
+        }
+    }
+}
+
+static unsigned hp_red_grid(int64_t n) {
+    int64_t g = (n + HP_RED_THREADS * 4 - 1) / (HP_RED_THREADS * 4);
+    if (g < 1) g = 1;
+    if (g > HP_RED_MAX_CTAS) g = HP_RED_MAX_CTAS;
+    return (unsigned)g;
+}
+
+// y += alpha x, alpha read from device memory (sign = -1 subtracts)
+__global__ void __launch_bounds__(256) hp_axpy_dev_kernel(int64_t n, const cplx* __restrict__ alpha, double sign,
+        const cplx* __restrict__ x, cplx* __restrict__ y) {
+    cplx a = cscale(sign, *alpha);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) y[e] = cfma(a, x[e], y[e]);
+}
+
+__global__ void __launch_bounds__(256) hp_axpy_kernel(int64_t n, cplx a, const cplx* __restrict__ x,
+        cplx* __restrict__ y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) y[e] = cfma(a, x[e], y[e]);
+}
+
+__global__ void __launch_bounds__(256) hp_scale_copy_kernel(int64_t n, cplx a, const cplx* __restrict__ x,
+        cplx* __restrict__ y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) y[e] = cmul(a, x[e]);
+}
+
+#define HP_COMBINE_MAX 32
+struct HpCombineArgs { cplx y[HP_COMBINE_MAX]; };
+__global__ void __launch_bounds__(256) hp_combine_kernel(int64_t n, int k, const cplx* __restrict__ V, int64_t ldv,
+        HpCombineArgs a, cplx* __restrict__ x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        cplx acc = x[e];
+        for (int j = 0; j < k; ++j) acc = cfma(a.y[j], V[(size_t)j * ldv + e], acc);
+        x[e] = acc;
+    }
+}
+
+static unsigned hp_ew_grid(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+extern "C" int hp_dotc(int64_t n, const double* x, const double* y, double* out, void* stream) {
+    if (hp_red_scratch()) return 2;
+    hp_reduce_kernel<0><<<hp_red_grid(n), HP_RED_THREADS, 0, (cudaStream_t)stream>>>(
+        n, (const cplx*)x, (const cplx*)y, g_partials, g_ticket, (cplx*)out);
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hp_nrm2(int64_t n, const double* x, double* out, void* stream) {
+    if (hp_red_scratch()) return 2;
+    hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, (cudaStream_t)stream>>>(
+        n, (const cplx*)x, (const cplx*)x, g_partials, g_ticket, (cplx*)out);
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hp_axpy(int64_t n, double a_re, double a_im, const double* x, double* y, void* stream) {
+    hp_axpy_kernel<<<hp_ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, cmake(a_re, a_im), (const cplx*)x, (cplx*)y);
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hp_scale_copy(int64_t n, double a_re, double a_im, const double* x, double* y, void* stream) {
+    hp_scale_copy_kernel<<<hp_ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, cmake(a_re, a_im), (const cplx*)x, (cplx*)y);
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hp_mgs(int64_t n, int k, const double* V, int64_t ldv, double* w, double* hcol, void* stream) {
+    if (hp_red_scratch()) return 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    cplx* h = (cplx*)hcol;
+    const cplx* Vc = (const cplx*)V;
+    hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, (const cplx*)w, (const cplx*)w, g_partials,
+                                                                  g_ticket, h + k + 1);       // h0
+    for (int j = 0; j < k; ++j) {
+        hp_reduce_kernel<0><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, Vc + (size_t)j * ldv, (const cplx*)w,
+                                                                      g_partials, g_ticket, h + j);
+        hp_axpy_dev_kernel<<<hp_ew_grid(n), 256, 0, st>>>(n, h + j, -1.0, Vc + (size_t)j * ldv, (cplx*)w);
+    }
+    hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, (const cplx*)w, (const cplx*)w, g_partials,
+                                                                  g_ticket, h + k);           // h1
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hp_combine(int64_t n, int k, const double* V, int64_t ldv, const double* y_host, double* x,
+                          void* stream) {
+    const cplx* Vc = (const cplx*)V;
+    for (int j0 = 0; j0 < k; j0 += HP_COMBINE_MAX) {
+        int kk = k - j0 < HP_COMBINE_MAX ? k - j0 : HP_COMBINE_MAX;
+        HpCombineArgs a;
+        for (int j = 0; j < kk; ++j) a.y[j] = cmake(y_host[2 * (j0 + j)], y_host[2 * (j0 + j) + 1]);
+        hp_combine_kernel<<<hp_ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, kk, Vc + (size_t)j0 * ldv, ldv, a,
+                                                                          (cplx*)x);
+    }
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -2,10 +2,18 @@
 //
 // Replaces the reference's algo2_3 (/root/reference/code.py:345-353): instead of a sparse LU of each
 // bn x bn strip operator H_m, the strip is treated as a block tridiagonal matrix over the x1 index
-// (b x b blocks) and the restriction T_m = (H_m^{-1})[last row, last row] is represented by
-//   * per leaf (<= QP consecutive block rows): samples of the Dirichlet-truncated leaf inverse,
-//   * per tree node: the 2b x 2b interface solve that merges two neighbouring segments.
-// tools/tree_prototype.py is the numpy model of exactly these arrays.
+// (b x b blocks D_i, diagonal couplings L_i = U_{i-1}) and the restriction
+// T_m = (H_m^{-1})[last row, last row] is represented by
+//   * P leaves (ranges of consecutive block rows) separated by P-1 single separator block rows;
+//     per leaf, samples of the Dirichlet-truncated leaf inverse G_l:
+//        W  [q][q]  = G_l[(c,b),(c',b)]
+//        Gf [b][q]  = cpl_left  * G_l[(first,k),(c,b)]     Gl [b][q] = cpl_right * G_l[(last,k),(c,b)]
+//   * the dense inverse N = S^{-1} of the separator Schur complement S (block tridiagonal, b x b blocks).
+// tools/strip_model.py is the numpy model of exactly these arrays.
+//
+// Every function here is the body of ONE thread of a setup kernel (csrc/hp_setup.cu); the loops over
+// leaf columns are written so that the lanes of a warp walk the leaf in lock step and read the same
+// b x b matrix at the same time (broadcast loads).
 #pragma once
 #include "hp_small.h"
 
@@ -59,8 +67,11 @@ HP_HD int hp_chain_backward(cplx* out, cplx* gcol, int i0, int i1, int m, const 
         for (int e = 0; e < bb; ++e) dst[e] = F[e];
         for (int k = 0; k < b; ++k) Lnext[k] = B.L[k];
     }
-    // diagonal blocks, ascending
-    cplx G[HP_BMAX * HP_BMAX], T1[HP_BMAX * HP_BMAX], T2[HP_BMAX * HP_BMAX];
+    // diagonal blocks, ascending; only the last column g_i = G_ii[:, b-1] is propagated:
+    //   g_i = Binv_i e + Binv_i L_i G_{i-1,i-1} U_{i-1} Binv_i e   needs the full G_{i-1,i-1}, so the
+    //   full block is carried in G.
+    cplx* G = F;
+    cplx T1[HP_BMAX * HP_BMAX], T2[HP_BMAX * HP_BMAX];
     cplx Uprev[HP_BMAX];
     for (int i = i0; i <= i1; ++i) {
         const cplx* Bi = out + (size_t)(i - 1) * bb;
@@ -80,55 +91,203 @@ HP_HD int hp_chain_backward(cplx* out, cplx* gcol, int i0, int i1, int m, const 
     return bad;
 }
 
-// Corner blocks of a segment [p..t]:  pp = G_pp, pt = G_pt, tp = G_tp, tt = G_tt  (each b x b)
-// Merge of segment 1 = [p..q] and segment 2 = [q+1..t]; cpl[k] = U_q[k] = L_{q+1}[k].
-// Node record: UP (4b x 2b) then DN (2b x 2b), see tools/tree_prototype.py::merge.
-HP_HD int hp_merge(cplx* rec, cplx* out_corners, const cplx* c1, const cplx* c2, const cplx* cpl, int b) {
-    const int bb = b * b, b2 = 2 * b;
-    const cplx *pp1 = c1, *pt1 = c1 + bb, *tp1 = c1 + 2 * bb, *tt1 = c1 + 3 * bb;
-    const cplx *pp2 = c2, *pt2 = c2 + bb, *tp2 = c2 + 2 * bb, *tt2 = c2 + 3 * bb;
-    cplx X[HP_BMAX * HP_BMAX], Y[HP_BMAX * HP_BMAX], K[HP_BMAX * HP_BMAX], KX[HP_BMAX * HP_BMAX],
-        YK[HP_BMAX * HP_BMAX];
-    for (int r = 0; r < b; ++r)
-        for (int s = 0; s < b; ++s) {
-            X[r * b + s] = cmul(tt1[r * b + s], cpl[s]);
-            Y[r * b + s] = cmul(pp2[r * b + s], cpl[s]);
+// x <- -M (d * x)  with M b x b row major, d a diagonal; y is scratch
+HP_HD void hp_propagate(cplx* x, const cplx* M, cplx dscale, const cplx* is2c, int b) {
+    cplx t[HP_BMAX], y[HP_BMAX];
+    for (int k = 0; k < b; ++k) t[k] = cmul(cmul(dscale, is2c[k]), x[k]);
+    for (int a = 0; a < b; ++a) {
+        cplx acc = cmake(0.0, 0.0);
+        for (int k = 0; k < b; ++k) acc = cfms(M[a * b + k], t[k], acc);
+        y[a] = acc;
+    }
+    for (int a = 0; a < b; ++a) x[a] = y[a];
+}
+
+// Column r (0-based inside the leaf, r < q) of the leaf generators.  The leaf covers block rows
+// i0..i0+q-1 (1-based).  Writes row r of W (wrow[0..q), W is symmetric), column r of Gf/Gl
+// (gf[k*gstride], gl[k*gstride]).  has_left/has_right: a separator exists on that side, the coupling
+// across the cut is folded into Gf/Gl; otherwise zeros are stored.  qloop >= q is the lock-step trip
+// count (the widest leaf), so that all lanes of a warp run the same loop.
+HP_HD void hp_leaf_column(cplx* wrow, cplx* gf, cplx* gl, size_t gstride, const cplx* Finv, const cplx* Binv,
+                          const cplx* gcol, int i0, int q, int qloop, int r, int m, int has_left, int has_right,
+                          const HpStripCtx& c) {
+    const int b = c.b, bb = b * b;
+    const bool live = r < q;
+    HpStripRow R;
+    hp_strip_rows(R, m, b, c.pml);
+    const cplx ih2 = cmake(1.0 / (c.pml.h * c.pml.h), 0.0);
+    cplx x0[HP_BMAX], x[HP_BMAX];
+    for (int k = 0; k < b; ++k) x0[k] = live ? gcol[(size_t)(i0 - 1 + r) * b + k] : cmake(0.0, 0.0);
+    if (live) wrow[r] = x0[b - 1];
+    // leftwards: x_col = -Finv[col] U_col x_{col+1},  U_i[k] = s1((i+.5)h) / (h^2 s2m(j_k h))
+    for (int k = 0; k < b; ++k) x[k] = x0[k];
+    for (int col = qloop - 2; col >= 0; --col) {
+        if (live && col < r) {
+            int i = i0 + col;
+            hp_propagate(x, Finv + (size_t)(i - 1) * bb, cmul(ih2, c.s1t[2 * i + 1]), R.is2c, b);
+            wrow[col] = x[b - 1];
         }
-    hp_gemm(K, X, Y, b, b, b, b, b, b, -1, 0);                     // K = -X Y
-    for (int r = 0; r < b; ++r) K[r * b + r].x += 1.0;             // I - X Y
-    int bad = hp_inv_inplace(K, b);
-    hp_gemm(KX, K, X, b, b, b, b, b, b, +1, 0);
-    hp_gemm(YK, Y, K, b, b, b, b, b, b, +1, 0);
-    cplx* UP = rec;
-    cplx* DN = rec + 8 * bb;
-    // Ua = diag(cpl) [K, -KX]   rows 0..b-1;   Uc = diag(cpl) [-YK, I + Y KX]   rows b..2b-1
-    for (int r = 0; r < b; ++r)
-        for (int s = 0; s < b; ++s) {
-            UP[r * b2 + s] = cmul(cpl[r], K[r * b + s]);
-            UP[r * b2 + b + s] = cneg(cmul(cpl[r], KX[r * b + s]));
-            UP[(b + r) * b2 + s] = cneg(cmul(cpl[r], YK[r * b + s]));
+    }
+    if (live) {
+        cplx sc = cmul(ih2, c.s1t[2 * i0 - 1]);            // L_{i0}[k] = s1((i0-.5)h)/(h^2 s2m)
+        for (int k = 0; k < b; ++k)
+            gf[(size_t)k * gstride] = has_left ? cmul(cmul(sc, R.is2c[k]), x[k]) : cmake(0.0, 0.0);
+    }
+    // rightwards: x_col = -Binv[col] L_col x_{col-1},  L_i[k] = s1((i-.5)h) / (h^2 s2m(j_k h))
+    for (int k = 0; k < b; ++k) x[k] = x0[k];
+    for (int col = 1; col < qloop; ++col) {
+        if (live && col > r && col < q) {
+            int i = i0 + col;
+            hp_propagate(x, Binv + (size_t)(i - 1) * bb, cmul(ih2, c.s1t[2 * i - 1]), R.is2c, b);
+            wrow[col] = x[b - 1];
         }
-    hp_gemm(X, Y, KX, b, b, b, b, b, b, +1, 0);                    // X := Y K X   (X no longer needed)
-    for (int r = 0; r < b; ++r)
-        for (int s = 0; s < b; ++s) {
-            cplx v = X[r * b + s];
-            if (r == s) v.x += 1.0;
-            UP[(b + r) * b2 + b + s] = cmul(cpl[r], v);
+    }
+    if (live) {
+        int it = i0 + q - 1;
+        cplx sc = cmul(ih2, c.s1t[2 * it + 1]);            // U_t[k]
+        for (int k = 0; k < b; ++k)
+            gl[(size_t)k * gstride] = has_right ? cmul(cmul(sc, R.is2c[k]), x[k]) : cmake(0.0, 0.0);
+    }
+}
+
+// Column kap of the corner block tp = G_l[(last,.),(first,kap)]: start from Binv[i0][:,kap] (= G_pp
+// column) and walk right.  out[a] = tp[a][kap], a < b.
+HP_HD void hp_leaf_corner_tp(cplx* out, const cplx* Binv, int i0, int q, int qloop, int kap, int m,
+                             const HpStripCtx& c) {
+    const int b = c.b, bb = b * b;
+    HpStripRow R;
+    hp_strip_rows(R, m, b, c.pml);
+    const cplx ih2 = cmake(1.0 / (c.pml.h * c.pml.h), 0.0);
+    cplx x[HP_BMAX];
+    const cplx* B0 = Binv + (size_t)(i0 - 1) * bb;
+    for (int a = 0; a < b; ++a) x[a] = B0[a * b + kap];
+    for (int col = 1; col < qloop; ++col) {
+        if (col < q) {
+            int i = i0 + col;
+            hp_propagate(x, Binv + (size_t)(i - 1) * bb, cmul(ih2, c.s1t[2 * i - 1]), R.is2c, b);
         }
-    // rows 2b..3b-1 = -pt1 * Uc ; rows 3b..4b-1 = -tp2 * Ua
-    hp_gemm(UP + (size_t)2 * b * b2, pt1, UP + (size_t)b * b2, b, b, b2, b2, b, b2, -1, 0);
-    hp_gemm(UP + (size_t)3 * b * b2, tp2, UP, b, b, b2, b2, b, b2, -1, 0);
-    // DN[:, :b] = -[Ua; Uc][:, :b] tp1 ;  DN[:, b:] = -[Ua; Uc][:, b:] pt2
-    hp_gemm(DN, UP, tp1, b2, b, b, b2, b2, b, -1, 0);
-    hp_gemm(DN + b, UP + b, pt2, b2, b, b, b2, b2, b, -1, 0);
-    // merged corners
-    cplx *pp = out_corners, *pt = out_corners + bb, *tp = out_corners + 2 * bb, *tt = out_corners + 3 * bb;
-    for (int e = 0; e < bb; ++e) { pp[e] = pp1[e]; tt[e] = tt2[e]; }
-    hp_gemm(pp, pt1, DN + (size_t)b * b2, b, b, b, b, b, b2, +1, 1);          // pp1 + pt1 DN[b:2b, :b]
-    hp_gemm(tp, tp2, DN, b, b, b, b, b, b2, +1, 0);                          // tp2 DN[0:b, :b]
-    hp_gemm(tt, tp2, DN + b, b, b, b, b, b, b2, +1, 1);                      // tt2 + tp2 DN[0:b, b:]
-    hp_gemm(pt, pt1, DN + (size_t)b * b2 + b, b, b, b, b, b, b2, +1, 0);      // pt1 DN[b:2b, b:]
+    }
+    for (int a = 0; a < b; ++a) out[a] = x[a];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Separator Schur complement.  Separator j sits at block row s (1-based); the leaf on its left ends at
+// s-1 (corner tt = Finv[s-1]) and the leaf on its right starts at s+1 (corner pp = Binv[s+1]).
+//   S_jj     = D_s - L_s tt_left U_{s-1} - U_s pp_right L_{s+1}
+//   S_j,j+1  = -U_s pt U_t           with pt = tp^T of the leaf between separators j and j+1 (t = s'-1)
+// ---------------------------------------------------------------------------------------------
+HP_HD void hp_sep_diag(cplx* S, int s, int m, const cplx* tt_left, const cplx* pp_right, const HpStripCtx& c) {
+    const int b = c.b;
+    HpStripRow R;
+    hp_strip_rows(R, m, b, c.pml);
+    HpBlockRow B;
+    hp_block_row(B, R, s, m, b, c.n, c.pml, c.s1t, c.is1t, c.c_mat, c.omega2);
+    for (int r = 0; r < b; ++r)
+        for (int t = 0; t < b; ++t) {
+            cplx v = cmake(0.0, 0.0);
+            if (r == t) v = B.dia[r];
+            else if (t == r - 1) v = B.sub[r];
+            else if (t == r + 1) v = B.sup[r];
+            // U_{s-1} = L_s and L_{s+1} = U_s
+            v = cfms(cmul(B.L[r], tt_left[r * b + t]), B.L[t], v);
+            v = cfms(cmul(B.U[r], pp_right[r * b + t]), B.U[t], v);
+            S[r * b + t] = v;
+        }
+}
+
+// S_{j,j+1}[a][c] = -U_s[a] tp[c][a] U_t[c]; s = separator j, s2 = separator j+1 (block rows, 1-based)
+HP_HD void hp_sep_offdiag(cplx* So, int s, int s2, int m, const cplx* tp, const HpStripCtx& c) {
+    const int b = c.b;
+    HpStripRow R;
+    hp_strip_rows(R, m, b, c.pml);
+    const cplx ih2 = cmake(1.0 / (c.pml.h * c.pml.h), 0.0);
+    cplx us = cmul(ih2, c.s1t[2 * s + 1]), ut = cmul(ih2, c.s1t[2 * s2 - 1]);
+    for (int a = 0; a < b; ++a)
+        for (int cc = 0; cc < b; ++cc) {
+            cplx v = cmul(cmul(cmul(us, R.is2c[a]), tp[cc * b + a]), cmul(ut, R.is2c[cc]));
+            So[a * b + cc] = cneg(v);
+        }
+}
+
+// Forward chain over the separators of one strip (dir = +1) or backward chain (dir = -1):
+//   fwd: X_j = S_jj - S_{j,j-1} Xinv_{j-1} S_{j-1,j},  Xinv_j,  Prop_j = -Xinv_j S_{j,j+1}
+//   bwd: X_j = S_jj - S_{j,j+1} Xinv_{j+1} S_{j+1,j},  Xinv_j,  Prop_j = -Xinv_j S_{j,j-1}
+// Sd [ns][b*b], So [ns-1][b*b] (So[j] = S_{j,j+1}; S_{j+1,j} is its transpose).
+// X, Xinv, Prop: [ns][b*b] each.
+HP_HD int hp_sep_chain(cplx* X, cplx* Xinv, cplx* Prop, const cplx* Sd, const cplx* So, int ns, int dir, int b) {
+    const int bb = b * b;
+    cplx F[HP_BMAX * HP_BMAX], T1[HP_BMAX * HP_BMAX], A[HP_BMAX * HP_BMAX];
+    int bad = 0;
+    for (int step = 0; step < ns; ++step) {
+        int j = dir > 0 ? step : ns - 1 - step;
+        for (int e = 0; e < bb; ++e) F[e] = Sd[(size_t)j * bb + e];
+        if (step > 0) {
+            int jp = j - dir;                                  // previous separator of the chain
+            // A = S_{j,jp}: fwd -> S_{j,j-1} = So[j-1]^T ; bwd -> S_{j,j+1} = So[j]
+            const cplx* o = So + (size_t)(dir > 0 ? j - 1 : j) * bb;
+            for (int r = 0; r < b; ++r)
+                for (int t = 0; t < b; ++t) A[r * b + t] = dir > 0 ? o[t * b + r] : o[r * b + t];
+            hp_gemm(T1, A, Xinv + (size_t)jp * bb, b, b, b, b, b, b, +1, 0);       // S_{j,jp} Xinv_jp
+            // F -= T1 * S_{jp,j} = T1 * A^T
+            for (int r = 0; r < b; ++r)
+                for (int t = 0; t < b; ++t) {
+                    cplx acc = F[r * b + t];
+                    for (int l = 0; l < b; ++l) acc = cfms(T1[r * b + l], A[t * b + l], acc);
+                    F[r * b + t] = acc;
+                }
+        }
+        for (int e = 0; e < bb; ++e) X[(size_t)j * bb + e] = F[e];
+        bad |= hp_inv_inplace(F, b);
+        for (int e = 0; e < bb; ++e) Xinv[(size_t)j * bb + e] = F[e];
+        int jn = j + dir;                                      // next separator of the chain
+        if (jn >= 0 && jn < ns) {
+            // Prop_j = -Xinv_j S_{j,jn}: fwd -> S_{j,j+1} = So[j] ; bwd -> S_{j,j-1} = So[j-1]^T
+            const cplx* o = So + (size_t)(dir > 0 ? j : j - 1) * bb;
+            for (int r = 0; r < b; ++r)
+                for (int t = 0; t < b; ++t) A[r * b + t] = dir > 0 ? o[r * b + t] : o[t * b + r];
+            hp_gemm(Prop + (size_t)j * bb, F, A, b, b, b, b, b, b, -1, 0);
+        }
+    }
     return bad;
+}
+
+// N_jj = (FX_j + BX_j - S_jj)^{-1}
+HP_HD int hp_sep_diag_inverse(cplx* Njj, const cplx* FX, const cplx* BX, const cplx* Sd, int b) {
+    cplx F[HP_BMAX * HP_BMAX];
+    for (int e = 0; e < b * b; ++e) F[e] = csub(cadd(FX[e], BX[e]), Sd[e]);
+    int bad = hp_inv_inplace(F, b);
+    for (int e = 0; e < b * b; ++e) Njj[e] = F[e];
+    return bad;
+}
+
+// Row (j, kap) of N (= column, N is symmetric): x_j = N_jj[:, kap]; x_{j'} = PF_{j'} x_{j'+1} upwards,
+// x_{j'} = PB_{j'} x_{j'-1} downwards.  nrow[0..ns*b) receives the row.  nsloop >= ns is the lock-step
+// trip count.
+HP_HD void hp_sep_row(cplx* nrow, const cplx* Njj, const cplx* PF, const cplx* PB, int ns, int j, int kap, int b) {
+    const int bb = b * b;
+    cplx x0[HP_BMAX], x[HP_BMAX], y[HP_BMAX];
+    const cplx* Nj = Njj + (size_t)j * bb;
+    for (int a = 0; a < b; ++a) { x0[a] = Nj[a * b + kap]; nrow[(size_t)j * b + a] = x0[a]; }
+    for (int a = 0; a < b; ++a) x[a] = x0[a];
+    for (int jj = j - 1; jj >= 0; --jj) {
+        const cplx* M = PF + (size_t)jj * bb;
+        for (int a = 0; a < b; ++a) {
+            cplx acc = cmake(0.0, 0.0);
+            for (int k = 0; k < b; ++k) acc = cfma(M[a * b + k], x[k], acc);
+            y[a] = acc;
+        }
+        for (int a = 0; a < b; ++a) { x[a] = y[a]; nrow[(size_t)jj * b + a] = y[a]; }
+    }
+    for (int a = 0; a < b; ++a) x[a] = x0[a];
+    for (int jj = j + 1; jj < ns; ++jj) {
+        const cplx* M = PB + (size_t)jj * bb;
+        for (int a = 0; a < b; ++a) {
+            cplx acc = cmake(0.0, 0.0);
+            for (int k = 0; k < b; ++k) acc = cfma(M[a * b + k], x[k], acc);
+            y[a] = acc;
+        }
+        for (int a = 0; a < b; ++a) { x[a] = y[a]; nrow[(size_t)jj * b + a] = y[a]; }
+    }
 }
 
 // coupling between block rows q and q+1 of strip m: U_q[k] = L_{q+1}[k] = 1/h^2 s1((q+.5)h)/s2m(j_k h)

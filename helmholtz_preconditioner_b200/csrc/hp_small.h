@@ -18,7 +18,7 @@ typedef double2 cplx;
 struct cplx { double x, y; };
 #endif
 
-#define HP_BMAX 16   // largest PML width (strip height) the small-matrix code is sized for
+#define HP_BMAX 24   // largest PML width (strip height) the small-matrix code is sized for
 
 HP_HD cplx cmake(double re, double im) { cplx r; r.x = re; r.y = im; return r; }
 HP_HD cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }

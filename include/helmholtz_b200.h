@@ -1,0 +1,101 @@
+/* helmholtz_b200.h -- C ABI of libhelmholtz_b200.so
+ *
+ * B200 (sm_100a) implementation of the data-parallel hot path of bocchs/helmholtz-preconditioner
+ * (reference: code.py).  Plain pointers and sizes only; no torch types.  Every entry point returns 0 on
+ * success and a non-zero code on failure (hp_last_error() gives the text).  Pointers named *_dev are
+ * device pointers on the solver's device; `stream` is a cudaStream_t passed as void* (NULL = default).
+ * Complex numbers are interleaved (re, im) doubles, i.e. numpy complex128 / double2.
+ *
+ * Vector layout: the field u has n*n entries, entry (j-1)*n + (i-1) is grid point (x1 index i, x2 index j),
+ * exactly the reference's f_mat.flatten() ordering (code.py:448).
+ *
+ * Each function cites the reference interface it replaces.
+ */
+#ifndef HELMHOLTZ_B200_H
+#define HELMHOLTZ_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hp_solver hp_solver;
+
+/* text of the last error raised on the calling thread */
+const char* hp_last_error(void);
+/* library/ABI version, and 1 if a usable CUDA device is present */
+int hp_version(void);
+int hp_device_ok(void);
+
+/* Problem definition.  Replaces the scalar set-up at code.py:442-447 (omega, h, eta) and keeps a device
+ * copy of the velocity model.  c_mat is the reference's (n+2) x (n+2) row-major float64 array (init_c*_mat,
+ * code.py:40-51); it is read as c_mat[i-1][j-1] like the reference does (code.py:108, 270).
+ * c_is_device != 0 means c_mat already lives on the device. */
+int hp_create(hp_solver** out, int n, int b, double omega_re, double omega_im, double cst,
+              const double* c_mat, int c_is_device, void* stream);
+int hp_destroy(hp_solver* s);
+
+/* ---- operator A ---------------------------------------------------------------------------------- */
+
+/* number of stored entries of A (5 n^2 - 4 n) */
+int64_t hp_csr_nnz(int n);
+/* build_A_matrix (code.py:202-219, with get_A_diag_block_coeffs :71-115, get_upper/lower_A_block :131-154):
+ * writes sorted CSR, indptr[n*n+1] and indices[nnz] int32 (scipy's index type here), data[nnz] complex128. */
+int hp_assemble_csr(hp_solver* s, int32_t* indptr_dev, int32_t* indices_dev, double* data_dev, void* stream);
+/* y = A x without forming A (the matvec scipy's gmres performs at code.py:516, iterative.py `matvec`) */
+int hp_stencil_matvec(hp_solver* s, const double* x_dev, double* y_dev, void* stream);
+/* y = A x from the assembled CSR arrays */
+int hp_csr_matvec(int64_t nrows, const int32_t* indptr_dev, const int32_t* indices_dev, const double* data_dev,
+                  const double* x_dev, double* y_dev, void* stream);
+
+/* ---- preconditioner ------------------------------------------------------------------------------ */
+
+/* algo2_3 (code.py:345-353): factor the front block H_F and every moving-PML strip H_m, m = m_lo..m_hi
+ * (b+1 <= m_lo <= m_hi <= n; pass 0,0 for all).  qmax (<= 64, 0 = default 64) bounds the leaf width of the
+ * x1 partition.  Strips outside [m_lo, m_hi] belong to other ranks of a slab decomposition. */
+int hp_precond_setup(hp_solver* s, int qmax, int m_lo, int m_hi, void* stream);
+/* bytes of device memory held by the factorisation */
+int64_t hp_precond_bytes(hp_solver* s);
+
+/* The three stages of algo2_4 (code.py:356-385), operating in place on the field u_dev (n*n complex):
+ *   hp_front_begin   : T_F u_F = H_F^{-1} u_F kept aside, u_{b+1} -= A_{b+1,F} T_F u_F        (:364-365)
+ *   hp_sweep_forward : for m = m_from..m_to     u_{m+1} -= A_{m+1,m} T_m u_m                   (:366-370)
+ *   hp_sweep_backward: for m = m_from..m_to (descending, m_from >= m_to), the diagonal solve (:372-375)
+ *                      fused with the upward elimination (:376-380):
+ *                        diag_mode 0 (reference): u_m <- u_m - T_m (u_m + A_{m,m+1} u_{m+1})
+ *                        diag_mode 1 (paper)    : u_m <- T_m (u_m - A_{m,m+1} u_{m+1})
+ *   hp_front_end     : u_F <- T_F u_F - H_F^{-1} A_{F,b+1} u_{b+1}                            (:381-384)
+ * hp_precond_apply runs all four on one device (u_dev <- M f_dev). */
+int hp_front_begin(hp_solver* s, double* u_dev, void* stream);
+int hp_sweep_forward(hp_solver* s, double* u_dev, int m_from, int m_to, void* stream);
+int hp_sweep_backward(hp_solver* s, double* u_dev, int m_from, int m_to, int diag_mode, void* stream);
+int hp_front_end(hp_solver* s, double* u_dev, void* stream);
+int hp_precond_apply(hp_solver* s, const double* f_dev, double* u_dev, int diag_mode, void* stream);
+/* y = T_m v : last n entries of H_m^{-1} [0; v]  (lu_Hm_ra[m-b-1].solve(u_temp)[-n:], code.py:370) */
+int hp_strip_apply(hp_solver* s, int m, const double* v_dev, double* y_dev, void* stream);
+/* copies of one strip's generators to host arrays (test hook): W[P*QP*QP], G[P*2*b*QP], nodes[(P-1)*12*b*b] */
+int hp_strip_layout(hp_solver* s, int* d, int* P, int* QP, int* leaf_start_host /* P+1, may be NULL */);
+int hp_strip_generators(hp_solver* s, int m, double* W_host, double* G_host, double* nodes_host);
+
+/* ---- Krylov vector kernels (scipy gmres inner loop, iterative.py; called from code.py:516) -------- */
+
+/* out_dev[0..1] = sum conj(x) y   (np.vdot) */
+int hp_dotc(int64_t n, const double* x_dev, const double* y_dev, double* out_dev, void* stream);
+/* out_dev[0] = ||x||_2 */
+int hp_nrm2(int64_t n, const double* x_dev, double* out_dev, void* stream);
+/* y += alpha x with alpha = (a_re, a_im) on the host */
+int hp_axpy(int64_t n, double a_re, double a_im, const double* x_dev, double* y_dev, void* stream);
+/* y = alpha x */
+int hp_scale_copy(int64_t n, double a_re, double a_im, const double* x_dev, double* y_dev, void* stream);
+/* Modified Gram-Schmidt of w against the rows V[0..k) (row stride ldv complex entries):
+ *   hcol_dev[2*j..] = vdot(V[j], w); w -= hcol[j] V[j]   sequentially for j = 0..k-1,
+ * then hcol_dev[2*k] = ||w|| (after) and hcol_dev[2*k+2] = ||w|| before orthogonalisation (h0). */
+int hp_mgs(int64_t n, int k, const double* V_dev, int64_t ldv, double* w_dev, double* hcol_dev, void* stream);
+/* x += sum_j y[j] V[j]   (x += y @ v[:col+1, :]); y on the host, 2*k doubles */
+int hp_combine(int64_t n, int k, const double* V_dev, int64_t ldv, const double* y_host, double* x_dev,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,5 +1,5 @@
 """csrc/hp_small.h + csrc/hp_setup_core.h compiled for the CPU (tests/host_harness.cpp) against the numpy
-model tools/tree_prototype.py.  These are the exact functions the setup kernels call per thread."""
+model tools/strip_model.py and the oracle.  These are the exact per-thread bodies the setup kernels run."""
 import ctypes
 import os
 import subprocess
@@ -8,12 +8,13 @@ import numpy as np
 import pytest
 
 from oracle import helmholtz_oracle as orc
-from tools import tree_prototype as tp
+from tools import strip_model as sm
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 C = ctypes
 cp = np.ctypeslib.ndpointer(dtype=np.complex128, flags="C_CONTIGUOUS")
 dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
 @pytest.fixture(scope="module")
@@ -23,10 +24,8 @@ def hh():
     subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(HERE, "host_harness.cpp")])
     lib = C.CDLL(so)
     lib.hh_tables.argtypes = [C.c_int] + [C.c_double] * 5 + [cp] * 4
-    lib.hh_leaf_chains.argtypes = [C.c_int] * 5 + [C.c_double] * 5 + [dp, cp, cp, cp]
-    lib.hh_merge.argtypes = [C.c_int, cp, cp, cp, cp, cp]
-    lib.hh_coupling.argtypes = [C.c_int] * 4 + [C.c_double] * 5 + [cp]
     lib.hh_inv.argtypes = [C.c_int, cp]
+    lib.hh_strip_setup.argtypes = [C.c_int] * 5 + [ip, ip, ip] + [C.c_double] * 5 + [dp, cp, cp, cp]
     return lib
 
 
@@ -37,12 +36,13 @@ def problem(n, b, wn, const):
 
 
 def rel(a, b):
-    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / np.linalg.norm(np.ravel(b))
+    d = np.linalg.norm(np.ravel(b))
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / (d if d > 0 else 1.0)
 
 
 def test_inverse(hh):
     rng = np.random.default_rng(0)
-    for b in (1, 2, 5, 12, 16):
+    for b in (1, 2, 5, 12, 16, 20, 24):
         A = rng.standard_normal((b, b)) + 1j * rng.standard_normal((b, b))
         if b > 1:
             A[0, 0] = 0  # force a row exchange
@@ -62,37 +62,43 @@ def test_tables(hh):
     assert rel(out[1] * out[0], np.ones_like(x)) < 1e-15
 
 
-@pytest.mark.parametrize("n,b,wn,const,qmax", [(45, 12, 6, 70, 8), (63, 12, 4, 61, 16), (40, 5, 4, 30, 64)])
-def test_chains_and_merge(hh, n, b, wn, const, qmax):
+def strip_setup(hh, p, c_mat, m, P):
+    n, b = p["n"], p["b"]
+    pt = sm.partition(n, P, 1)
+    QP, ns = pt["QP"], P - 1
+    W = np.zeros((P, QP, QP), np.complex128)
+    G = np.zeros((P, 2, b, QP), np.complex128)
+    N = np.zeros((max(ns * b, 1), max(ns * b, 1)), np.complex128)
+    bad = hh.hh_strip_setup(n, b, m, P, QP, pt["leaf_start"].astype(np.int32), pt["q"].astype(np.int32),
+                            np.ascontiguousarray(pt["sep"].astype(np.int32)) if ns else np.zeros(1, np.int32),
+                            p["const"], p["eta"], p["h"], p["omega"].real, p["omega"].imag,
+                            np.ascontiguousarray(c_mat), W, G, N)
+    assert bad == 0
+    return pt, W, G, N
+
+
+@pytest.mark.parametrize("n,b,wn,const,P", [(45, 12, 6, 70, 4), (63, 12, 4, 61, 5), (40, 5, 4, 30, 1),
+                                            (40, 5, 4, 30, 7), (50, 20, 5, 60, 3)])
+def test_strip_generators(hh, n, b, wn, const, P):
     p, c_mat = problem(n, b, wn, const)
-    c_mat = np.ascontiguousarray(c_mat)
     for m in (b + 1, (n + b) // 2, n):
-        tree = tp.StripTree(m, c_mat=c_mat, qmax=qmax, **p)
-        st = tree.start
-        Finv = np.zeros((n, b * b), np.complex128)
-        Binv = np.zeros((n, b * b), np.complex128)
-        gcol = np.zeros((n, b), np.complex128)
-        for l in range(tree.P):
-            bad = hh.hh_leaf_chains(n, b, m, int(st[l]) + 1, int(st[l + 1]), p["const"], p["eta"], p["h"],
-                                    p["omega"].real, p["omega"].imag, c_mat, Finv, Binv, gcol)
-            assert bad == 0
-            lf = tree.leaves[l]
-            sl = slice(st[l], st[l + 1])
-            assert rel(Finv[sl], lf["Finv"].reshape(-1, b * b)) < 1e-12
-            assert rel(Binv[sl], lf["Binv"].reshape(-1, b * b)) < 1e-12
-            assert rel(gcol[sl], lf["gcol"]) < 1e-12
-        # merges, level by level, fed with the prototype's corners
-        for lv in range(1, tree.d + 1):
-            for t in range(tree.P >> lv):
-                c1, c2 = tree.corners[lv - 1][2 * t], tree.corners[lv - 1][2 * t + 1]
-                pack = lambda c: np.ascontiguousarray(np.stack([c["pp"], c["pt"], c["tp"], c["tt"]]))  # noqa: E731
-                q1 = int(st[(2 * t + 1) << (lv - 1)])            # 0-based first row of right child = q (1-based)
-                cpl = np.zeros(b, np.complex128)
-                hh.hh_coupling(n, b, m, q1, p["const"], p["eta"], p["h"], p["omega"].real, p["omega"].imag, cpl)
-                assert rel(cpl, tree.U[q1 - 1]) < 1e-14 and rel(cpl, tree.L[q1]) < 1e-14
-                rec = np.zeros(12 * b * b, np.complex128)
-                corners = np.zeros((4, b, b), np.complex128)
-                assert hh.hh_merge(b, pack(c1), pack(c2), cpl, rec, corners) == 0
-                assert rel(rec, tree.nodes[tree.lvoff[lv] + t]) < 1e-11
-                me = tree.corners[lv][t]
-                assert rel(corners, np.stack([me["pp"], me["pt"], me["tp"], me["tt"]])) < 1e-11
+        pt, W, G, N = strip_setup(hh, p, c_mat, m, P)
+        mod = sm.StripModel(m, c_mat=c_mat, P=P, **p)
+        assert rel(W, mod.W) < 1e-11
+        assert rel(G, mod.G) < 1e-11
+        if P > 1:
+            assert rel(N, mod.N) < 1e-11
+
+
+def test_strip_apply_medium(hh):
+    """n = 200: T_m v from the C++ generators against the oracle's splu solve (code.py:368-370)."""
+    n, b, P = 200, 12, 6
+    p, c_mat = problem(n, b, 20, 80)
+    Pc = orc.SweepingPreconditioner(c_mat=c_mat, **p)
+    rng = np.random.default_rng(1)
+    for m in (b + 1, 117, n):
+        pt, W, G, N = strip_setup(hh, p, c_mat, m, P)
+        mod = sm.StripModel.__new__(sm.StripModel)
+        mod.b, mod.n, mod.m, mod.part, mod.W, mod.G, mod.N = b, n, m, pt, W, G, N
+        v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        assert rel(mod.apply(v), Pc.T(m, v)) < 1e-12
