@@ -1,0 +1,127 @@
+// C ABI glue of libhelmholtz_b200.so: solver life cycle, error text, algo2_3/algo2_4 drivers.
+#include "hp_internal.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+static thread_local char g_err[1024] = "";
+
+void hp_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* hp_last_error(void) { return g_err; }
+extern "C" int hp_version(void) { return 100; }
+
+extern "C" int hp_device_ok(void) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { cudaGetLastError(); return 0; }
+    return 1;
+}
+
+extern "C" int hp_create(hp_solver** out, int n, int b, double omega_re, double omega_im, double cst,
+                         const double* c_mat, int c_is_device, void* stream) {
+    if (!out) { hp_set_error("hp_create: null output"); return 1; }
+    *out = nullptr;
+    if (n < 2 || b < 1 || b > HP_BMAX || b > n) {
+        hp_set_error("hp_create: need 2 <= n, 1 <= b <= min(n, %d); got n=%d b=%d", HP_BMAX, n, b);
+        return 1;
+    }
+    if (!hp_device_ok()) { hp_set_error("hp_create: no CUDA device (this library has no CPU path)"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    hp_solver* s = new hp_solver();
+    s->n = n; s->b = b;
+    double h = 1.0 / (double)(n + 1);                     // code.py:443
+    s->pml.cst = cst; s->pml.h = h; s->pml.eta = (double)b * h;   // code.py:444
+    s->pml.omega = cmake(omega_re, omega_im);             // code.py:442
+    s->omega2 = cmul(s->pml.omega, s->pml.omega);
+    int dev = 0;
+    HP_CUDA(cudaGetDevice(&dev));
+    HP_CUDA(cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, dev));
+    size_t tl = sizeof(cplx) * (size_t)(2 * n + 3);
+    HP_CUDA(cudaMalloc(&s->s1t, tl)); HP_CUDA(cudaMalloc(&s->is1t, tl));
+    HP_CUDA(cudaMalloc(&s->s2t, tl)); HP_CUDA(cudaMalloc(&s->is2t, tl));
+    size_t cb = sizeof(double) * (size_t)(n + 2) * (n + 2);
+    HP_CUDA(cudaMalloc(&s->c_mat, cb));
+    HP_CUDA(cudaMalloc(&s->kappa, sizeof(double) * (size_t)n * n));
+    HP_CUDA(cudaMalloc(&s->status, sizeof(int)));
+    HP_CUDA(cudaMemsetAsync(s->status, 0, sizeof(int), st));
+    HP_CUDA(cudaMemcpyAsync(s->c_mat, c_mat, cb, c_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (hp_launch_tables(s, st)) return 2;
+    s->s2t_h.resize(2 * n + 3);
+    HP_CUDA(cudaMemcpyAsync(s->s2t_h.data(), s->s2t, tl, cudaMemcpyDeviceToHost, st));
+    HP_CUDA(cudaStreamSynchronize(st));
+    *out = s;
+    return 0;
+}
+
+extern "C" int hp_destroy(hp_solver* s) {
+    if (!s) return 0;
+    hp_free_strips(s);
+    cudaFree(s->s1t); cudaFree(s->is1t); cudaFree(s->s2t); cudaFree(s->is2t);
+    cudaFree(s->c_mat); cudaFree(s->kappa); cudaFree(s->status);
+    cudaFree(s->f_low); cudaFree(s->f_invd); cudaFree(s->f_up); cudaFree(s->TF);
+    delete s;
+    return 0;
+}
+
+extern "C" int hp_precond_setup(hp_solver* s, int P, int K, int m_lo, int m_hi, void* stream) {
+    if (!s) { hp_set_error("hp_precond_setup: null solver"); return 1; }
+    if (m_lo == 0 && m_hi == 0) { m_lo = s->b + 1; m_hi = s->n; }
+    if (m_lo < s->b + 1 || m_hi > s->n) {
+        hp_set_error("hp_precond_setup: strips must lie in %d..%d, got %d..%d", s->b + 1, s->n, m_lo, m_hi);
+        return 1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (hp_front_setup(s, st)) return 2;
+    if (m_lo > m_hi) { hp_free_strips(s); return 0; }     // a rank that holds no strip (front block only)
+    return hp_setup_strips(s, P, K, m_lo, m_hi, st);
+}
+
+extern "C" int64_t hp_precond_bytes(hp_solver* s) { return s ? s->bytes : 0; }
+extern "C" double hp_precond_setup_ms(hp_solver* s) { return s ? s->setup_ms : 0.0; }
+
+extern "C" int hp_precond_apply(hp_solver* s, const double* f_dev, double* u_dev, int diag_mode, void* stream) {
+    if (!s) { hp_set_error("hp_precond_apply: null solver"); return 1; }
+    if (s->m_lo != s->b + 1 || s->m_hi != s->n) {
+        if (!(s->b == s->n)) {
+            hp_set_error("hp_precond_apply: solver holds strips %d..%d, needs %d..%d (use the staged calls for slabs)",
+                         s->m_lo, s->m_hi, s->b + 1, s->n);
+            return 1;
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = s->n, b = s->b;
+    if (f_dev != u_dev)
+        HP_CUDA(cudaMemcpyAsync(u_dev, f_dev, sizeof(cplx) * (size_t)n * n, cudaMemcpyDeviceToDevice, st));
+    int rc;
+    if ((rc = hp_front_begin(s, u_dev, stream))) return rc;
+    if (b < n) {
+        if ((rc = hp_sweep_forward(s, u_dev, b + 1, n - 1, stream))) return rc;
+        if ((rc = hp_sweep_backward(s, u_dev, n, b + 1, diag_mode, stream))) return rc;
+    }
+    return hp_front_end(s, u_dev, stream);
+}
+
+extern "C" int hp_strip_layout(hp_solver* s, int* P, int* K, int* QP, int* CW, int* NS, int* NR, int64_t* PK,
+                               int* leaf_start_host, int* leaf_q_host, int* sep_host) {
+    if (!s || !s->packets) { hp_set_error("hp_strip_layout: preconditioner not set up"); return 1; }
+    const HpLayout& L = s->lay;
+    if (P) *P = L.P; if (K) *K = L.K; if (QP) *QP = L.QP; if (CW) *CW = L.CW;
+    if (NS) *NS = L.NS; if (NR) *NR = L.NR; if (PK) *PK = (int64_t)L.PK;
+    if (leaf_start_host) memcpy(leaf_start_host, s->leaf_start_h.data(), sizeof(int) * L.P);
+    if (leaf_q_host) memcpy(leaf_q_host, s->leaf_q_h.data(), sizeof(int) * L.P);
+    if (sep_host && L.P > 1) memcpy(sep_host, s->sep_h.data(), sizeof(int) * (L.P - 1));
+    return 0;
+}
+
+extern "C" int hp_strip_packets(hp_solver* s, int m, double* packets_host) {
+    if (!s || !s->packets) { hp_set_error("hp_strip_packets: preconditioner not set up"); return 1; }
+    if (m < s->m_lo || m > s->m_hi) { hp_set_error("hp_strip_packets: strip %d not held", m); return 1; }
+    size_t cnt = (size_t)s->lay.G * s->lay.PK;
+    HP_CUDA(cudaMemcpy(packets_host, s->packets + (size_t)(m - s->m_lo) * cnt, cnt * sizeof(cplx), cudaMemcpyDeviceToHost));
+    return 0;
+}

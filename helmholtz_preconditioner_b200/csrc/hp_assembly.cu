@@ -93,13 +93,16 @@ __global__ void __launch_bounds__(256) hp_assemble_csr_kernel(int n, double ih2,
 // x1-dependent factors in registers for the whole march.  Algorithmic traffic per grid point:
 // x 16 B read + y 16 B written + kappa 8 B read = 40 B.
 #define HP_SPMV_ROWS 16
-__global__ void __launch_bounds__(128) hp_stencil_matvec_kernel(int n, double ih2, cplx omega2,
+// Rows j_lo <= j < j_hi (0-based) of the grid: x and y hold those rows only (slab storage); the rows just
+// outside come from the halo pointers x_south (row j_lo-1) and x_north (row j_hi), NULL on the grid boundary.
+__global__ void __launch_bounds__(128) hp_stencil_matvec_kernel(int n, int j_lo, int j_hi, double ih2, cplx omega2,
         const cplx* __restrict__ s1t, const cplx* __restrict__ is1t, const cplx* __restrict__ s2t,
         const cplx* __restrict__ is2t, const double* __restrict__ kappa,
-        const cplx* __restrict__ x, cplx* __restrict__ y) {
+        const cplx* __restrict__ x, const cplx* __restrict__ x_south, const cplx* __restrict__ x_north,
+        cplx* __restrict__ y) {
     const int col = blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const int j0 = blockIdx.y * HP_SPMV_ROWS;
+    const int j0 = j_lo + blockIdx.y * HP_SPMV_ROWS;
     const bool act = col < n;
     const cplx zero = cmake(0.0, 0.0);
     cplx aW = zero, aE = zero, dI = zero, wI = zero;
@@ -109,15 +112,23 @@ __global__ void __launch_bounds__(128) hp_stencil_matvec_kernel(int n, double ih
         dI = is1t[2 * col + 2];                   // 1/s1(ih)
         wI = cmul(omega2, dI);
     }
-    cplx xS = (act && j0 > 0) ? x[(size_t)(j0 - 1) * n + col] : zero;
-    cplx xC = act ? x[(size_t)j0 * n + col] : zero;
+    cplx xS = zero;
+    if (act) {
+        if (j0 > j_lo) xS = x[(size_t)(j0 - 1 - j_lo) * n + col];
+        else if (x_south) xS = x_south[col];
+    }
+    cplx xC = act ? x[(size_t)(j0 - j_lo) * n + col] : zero;
 #pragma unroll 4
     for (int r = 0; r < HP_SPMV_ROWS; ++r) {
         const int j = j0 + r;                       // 0-based grid row, uniform over the CTA
-        if (j >= n) break;
-        const size_t base = (size_t)j * n;
-        cplx xN = (act && j + 1 < n) ? x[base + n + col] : zero;
-        double kap = act ? kappa[base + col] : 0.0;
+        if (j >= j_hi) break;
+        const size_t base = (size_t)(j - j_lo) * n;
+        cplx xN = zero;
+        if (act) {
+            if (j + 1 < j_hi) xN = x[base + n + col];
+            else if (x_north) xN = x_north[col];
+        }
+        double kap = act ? kappa[(size_t)j * n + col] : 0.0;
         cplx xW, xE;
         xW.x = __shfl_up_sync(0xffffffffu, xC.x, 1);
         xW.y = __shfl_up_sync(0xffffffffu, xC.y, 1);
@@ -163,14 +174,22 @@ extern "C" int hp_assemble_csr(hp_solver* s, int32_t* indptr, int32_t* indices, 
     return 0;
 }
 
-extern "C" int hp_stencil_matvec(hp_solver* s, const double* x, double* y, void* stream) {
+extern "C" int hp_stencil_matvec_rows(hp_solver* s, int j_lo, int j_hi, const double* x, const double* x_south,
+                                      const double* x_north, double* y, void* stream) {
     if (!s) { hp_set_error("hp_stencil_matvec: null solver"); return 1; }
+    if (j_lo < 0 || j_hi > s->n || j_lo >= j_hi) { hp_set_error("hp_stencil_matvec_rows: bad row range %d..%d", j_lo, j_hi); return 1; }
     double ih2 = 1.0 / (s->pml.h * s->pml.h);
-    dim3 grd((s->n + 127) / 128, (s->n + HP_SPMV_ROWS - 1) / HP_SPMV_ROWS);
+    dim3 grd((s->n + 127) / 128, (j_hi - j_lo + HP_SPMV_ROWS - 1) / HP_SPMV_ROWS);
     hp_stencil_matvec_kernel<<<grd, 128, 0, (cudaStream_t)stream>>>(
-        s->n, ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa, (const cplx*)x, (cplx*)y);
+        s->n, j_lo, j_hi, ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa, (const cplx*)x,
+        (const cplx*)x_south, (const cplx*)x_north, (cplx*)y);
     HP_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int hp_stencil_matvec(hp_solver* s, const double* x, double* y, void* stream) {
+    if (!s) { hp_set_error("hp_stencil_matvec: null solver"); return 1; }
+    return hp_stencil_matvec_rows(s, 0, s->n, x, nullptr, nullptr, y, stream);
 }
 
 extern "C" int hp_csr_matvec(int64_t nrows, const int32_t* indptr, const int32_t* indices, const double* data,

@@ -7,9 +7,7 @@
 #include <vector>
 
 #include "hp_setup_core.h"
-
-#define HP_QMAX 64          // widest leaf (block rows) of the x1 partition
-#define HP_MAX_LEVELS 12    // up to 4096 leaves
+#include "../../include/helmholtz_b200.h"
 
 void hp_set_error(const char* fmt, ...);
 
@@ -22,6 +20,23 @@ void hp_set_error(const char* fmt, ...);
         }                                                                                          \
     } while (0)
 
+// x1 partition of every strip and the packed generator layout ("packets").
+//
+// The sweep kernel runs G = P*K CTAs; CTA g = l*K + k owns part k of leaf l (columns part c0..c1-1) and the
+// rows [g*NR, (g+1)*NR) of the separator inverse N.  Per strip and CTA one contiguous packet of PK complex
+// numbers holds everything that CTA streams for that strip:
+//     Wp [CW][QP]   rows c0..c1-1 of W_l (zero padded)
+//     Gp [2b][CW]   columns c0..c1-1 of [Gf_l; Gl_l]
+//     Np [NR][NSP]  its rows of N
+// Strip m (m_lo <= m <= m_hi) starts at packets + (m - m_lo) * G * PK.
+struct HpLayout {
+    int P = 0, K = 0, G = 0;     // leaves, parts per leaf, CTAs
+    int QP = 0, CW = 0;          // widest leaf, widest part
+    int NS = 0, NSP = 0, NR = 0; // separator unknowns b*(P-1), padded row length, rows of N per CTA
+    size_t PK = 0;               // complex numbers per packet
+    size_t offG = 0, offN = 0;   // offsets of Gp and Np inside a packet
+};
+
 struct hp_solver {
     int n = 0, b = 0;
     HpPml pml;
@@ -29,37 +44,40 @@ struct hp_solver {
     int num_sms = 0;
     // operator tables on the half grid t = 0..2n+2 (unshifted PML)
     cplx *s1t = nullptr, *is1t = nullptr, *s2t = nullptr, *is2t = nullptr;
+    std::vector<cplx> s2t_h;      // host copy of s2t (couplings between grid rows are formed on the host)
     double* c_mat = nullptr;      // (n+2)^2 as given
     double* kappa = nullptr;      // n*n, kappa[(j-1)*n + (i-1)] = 1 / c_mat[i-1][j-1]^2  (grid-aligned)
     // strip factorisation
-    int d = 0, P = 0, QP = 0;     // tree depth, leaves, padded leaf width
+    HpLayout lay;
     int m_lo = 0, m_hi = -1;      // strips held by this solver
-    std::vector<int> leaf_start_h;
-    int* leaf_start = nullptr;    // device, P+1 (0-based first block row of each leaf)
-    int lvoff[HP_MAX_LEVELS + 2];
-    cplx *W = nullptr, *G = nullptr, *nodes = nullptr;
-    size_t W_stride = 0, G_stride = 0, N_stride = 0;   // complex entries per strip
+    std::vector<int> leaf_start_h, leaf_q_h, sep_h;
+    int *leaf_start = nullptr, *leaf_q = nullptr, *sep = nullptr;   // device copies
+    cplx* packets = nullptr;
     int64_t bytes = 0;
+    double setup_ms = 0.0;
     // front block: Thomas factors of the b tridiagonal diagonal blocks (reference H_F)
-    cplx *fw = nullptr, *finvd = nullptr, *fup = nullptr;   // [b][n]
-    cplx* TF = nullptr;                                      // [b][n]   T_F u_F kept between the stages
-    cplx* ztmp = nullptr;                                    // [2][n]
-    // sweep scratch (tree exchange)
-    cplx *seg = nullptr, *xi = nullptr, *ext = nullptr;
-    int sweep_ctas = 0, sweep_lpc = 0;
+    cplx *f_low = nullptr, *f_invd = nullptr, *f_up = nullptr;   // [b][n]
+    cplx* TF = nullptr;                                           // [b][n]   T_F u_F kept between the stages
+    // sweep scratch
+    cplx *vbuf = nullptr, *gparts = nullptr, *xs = nullptr;
+    unsigned int* bar = nullptr;
     int* status = nullptr;        // device flag: non-zero when a pivot vanished during setup
 };
 
-struct HpCtxDev {   // by-value kernel argument
+static inline HpStripCtx hp_ctx(const hp_solver* s) {
     HpStripCtx c;
-};
+    c.n = s->n; c.b = s->b; c.pml = s->pml; c.omega2 = s->omega2;
+    c.s1t = s->s1t; c.is1t = s->is1t; c.c_mat = s->c_mat;
+    return c;
+}
 
 // hp_assembly.cu
 int hp_launch_tables(hp_solver* s, cudaStream_t st);
 // hp_setup.cu
-int hp_setup_strips(hp_solver* s, int qmax, int m_lo, int m_hi, cudaStream_t st);
+int hp_setup_strips(hp_solver* s, int P, int K, int m_lo, int m_hi, cudaStream_t st);
 void hp_free_strips(hp_solver* s);
 // hp_front.cu
 int hp_front_setup(hp_solver* s, cudaStream_t st);
-// hp_sweep.cu
-int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout, int m_from, int m_to, cudaStream_t st);
+// hp_sweep.cu : mode 0 = forward, 1 = backward, 2 = single strip apply (vin -> yout)
+int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout, int m_from, int m_to,
+                    int diag_mode, cudaStream_t st);

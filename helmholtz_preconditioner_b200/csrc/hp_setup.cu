@@ -1,0 +1,281 @@
+// Setup of the strip solves: algo2_3 of the reference (/root/reference/code.py:345-353) for the strips
+// H_m, m = m_lo..m_hi.  Where the reference calls SuperLU on each bn x bn strip operator, every strip is
+// reduced here to the generators the sweep kernel streams (csrc/hp_setup_core.h, tools/strip_model.py):
+//   leaf samples W, Gf, Gl and the dense separator inverse N, written straight into the per-CTA packets.
+// Strips are independent; they are processed in batches of LB strips so that the scratch (the Schur
+// chains of every block row) stays bounded.
+#include "hp_internal.cuh"
+
+#include <algorithm>
+
+struct HpSetupArgs {
+    HpStripCtx c;
+    HpLayout lay;
+    const int *leaf_start, *leaf_q, *sep;
+    int m0;            // first strip of this batch
+    int nb;            // strips in this batch
+    int m_lo;          // first strip of the solver (packet index origin)
+    cplx *Finv, *Binv, *gcol;             // [nb][n][bb], [nb][n][bb], [nb][n][b]
+    cplx* tp;                             // [nb][P][bb]
+    cplx *Sd, *So, *FX, *FXi, *PF, *BX, *BXi, *PB, *Njj;   // [nb][max(ns,1)][bb]
+    cplx* packets;
+    int* status;
+};
+
+__device__ __forceinline__ cplx* hp_packet(const HpSetupArgs& a, int layer_in_batch, int g) {
+    return a.packets + ((size_t)(a.m0 - a.m_lo + layer_in_batch) * a.lay.G + g) * a.lay.PK;
+}
+
+// thread -> (strip, leaf, direction)
+__global__ void __launch_bounds__(64) hp_chain_kernel(HpSetupArgs a) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = a.nb * a.lay.P * 2;
+    if (t >= total) return;
+    int dir = t & 1, l = (t >> 1) % a.lay.P, lb = (t >> 1) / a.lay.P;
+    int m = a.m0 + lb, n = a.c.n, bb = a.c.b * a.c.b;
+    int i0 = a.leaf_start[l] + 1, i1 = a.leaf_start[l] + a.leaf_q[l];
+    int bad;
+    if (dir == 0) bad = hp_chain_forward(a.Finv + (size_t)lb * n * bb, i0, i1, m, a.c);
+    else bad = hp_chain_backward(a.Binv + (size_t)lb * n * bb, a.gcol + (size_t)lb * n * a.c.b, i0, i1, m, a.c);
+    if (bad) atomicOr(a.status, 1);
+}
+
+// CTA -> (strip, leaf); thread -> leaf column r
+__global__ void hp_leaf_kernel(HpSetupArgs a) {
+    int l = blockIdx.x % a.lay.P, lb = blockIdx.x / a.lay.P;
+    int r = threadIdx.x;
+    int m = a.m0 + lb, n = a.c.n, b = a.c.b, bb = b * b;
+    int q = a.leaf_q[l], K = a.lay.K;
+    int rr = r < q ? r : q - 1;
+    int k = ((rr + 1) * K - 1) / q;                    // part that owns column rr
+    int lc0 = (q * k) / K;
+    cplx* pk = hp_packet(a, lb, l * K + k);
+    cplx* wrow = pk + (size_t)(rr - lc0) * a.lay.QP;
+    cplx* gf = pk + a.lay.offG + (rr - lc0);
+    cplx* gl = gf + (size_t)b * a.lay.CW;
+    hp_leaf_column(wrow, gf, gl, a.lay.CW, a.Finv + (size_t)lb * n * bb, a.Binv + (size_t)lb * n * bb,
+                   a.gcol + (size_t)lb * n * b, a.leaf_start[l] + 1, q, a.lay.QP, r, m, l > 0, l < a.lay.P - 1, a.c);
+}
+
+// thread -> (strip, inner leaf, column kap of tp)
+__global__ void __launch_bounds__(128) hp_corner_kernel(HpSetupArgs a) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = a.c.b, P = a.lay.P, bb = b * b;
+    int total = a.nb * P * b;
+    if (t >= total) return;
+    int kap = t % b, l = (t / b) % P, lb = t / (b * P);
+    if (l == 0 || l == P - 1) return;
+    cplx col[HP_BMAX];
+    hp_leaf_corner_tp(col, a.Binv + (size_t)lb * a.c.n * bb, a.leaf_start[l] + 1, a.leaf_q[l], a.lay.QP, kap,
+                      a.m0 + lb, a.c);
+    cplx* tp = a.tp + ((size_t)lb * P + l) * bb;
+    for (int r = 0; r < b; ++r) tp[r * b + kap] = col[r];
+}
+
+// thread -> (strip, separator)
+__global__ void __launch_bounds__(128) hp_sep_blocks_kernel(HpSetupArgs a) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int ns = a.lay.P - 1, b = a.c.b, bb = b * b, n = a.c.n;
+    if (t >= a.nb * ns) return;
+    int j = t % ns, lb = t / ns, m = a.m0 + lb;
+    int s = a.sep[j] + 1;
+    const cplx* Finv = a.Finv + (size_t)lb * n * bb;
+    const cplx* Binv = a.Binv + (size_t)lb * n * bb;
+    hp_sep_diag(a.Sd + ((size_t)lb * ns + j) * bb, s, m, Finv + (size_t)(s - 2) * bb, Binv + (size_t)s * bb, a.c);
+    if (j + 1 < ns)
+        hp_sep_offdiag(a.So + ((size_t)lb * ns + j) * bb, s, a.sep[j + 1] + 1, m,
+                       a.tp + ((size_t)lb * a.lay.P + j + 1) * bb, a.c);
+}
+
+// thread -> (strip, direction)
+__global__ void __launch_bounds__(32) hp_sep_chain_kernel(HpSetupArgs a) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int ns = a.lay.P - 1, bb = a.c.b * a.c.b;
+    if (t >= a.nb * 2) return;
+    int dir = t & 1, lb = t >> 1;
+    size_t o = (size_t)lb * ns * bb;
+    int bad;
+    if (dir == 0) bad = hp_sep_chain(a.FX + o, a.FXi + o, a.PF + o, a.Sd + o, a.So + o, ns, +1, a.c.b);
+    else bad = hp_sep_chain(a.BX + o, a.BXi + o, a.PB + o, a.Sd + o, a.So + o, ns, -1, a.c.b);
+    if (bad) atomicOr(a.status, 2);
+}
+
+// thread -> (strip, separator)
+__global__ void __launch_bounds__(64) hp_sep_diaginv_kernel(HpSetupArgs a) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int ns = a.lay.P - 1, bb = a.c.b * a.c.b;
+    if (t >= a.nb * ns) return;
+    size_t o = (size_t)t * bb;
+    if (hp_sep_diag_inverse(a.Njj + o, a.FX + o, a.BX + o, a.Sd + o, a.c.b)) atomicOr(a.status, 4);
+}
+
+// thread -> (strip, separator, component): one row of N, written into the packet of the CTA that owns it
+__global__ void __launch_bounds__(128) hp_sep_rows_kernel(HpSetupArgs a) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int ns = a.lay.P - 1, b = a.c.b, bb = b * b;
+    if (t >= a.nb * ns * b) return;
+    int kap = t % b, j = (t / b) % ns, lb = t / (b * ns);
+    int row = j * b + kap;
+    cplx* pk = hp_packet(a, lb, row / a.lay.NR);
+    cplx* nrow = pk + a.lay.offN + (size_t)(row % a.lay.NR) * a.lay.NSP;
+    size_t o = (size_t)lb * ns * bb;
+    hp_sep_row(nrow, a.Njj + o, a.PF + o, a.PB + o, ns, j, kap, b);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// partition
+// ------------------------------------------------------------------------------------------------------
+static void hp_fill_layout(HpLayout& L, int n, int b, int P, int K) {
+    int inner = n - (P - 1);
+    L.P = P; L.K = K; L.G = P * K;
+    L.QP = (inner + P - 1) / P;
+    L.CW = (L.QP + K - 1) / K;
+    L.NS = b * (P - 1);
+    L.NSP = L.NS > 0 ? L.NS : 1;
+    L.NR = L.NS > 0 ? (L.NS + L.G - 1) / L.G : 0;
+    L.offG = (size_t)L.CW * L.QP;
+    L.offN = L.offG + (size_t)2 * b * L.CW;
+    L.PK = L.offN + (size_t)L.NR * L.NSP;
+}
+
+// Choose (P, K): the sweep streams one packet per CTA and strip, so the per-CTA packet size is the time
+// per strip; among the candidates that fit in memory take the smallest packet.
+static int hp_choose_layout(hp_solver* s, int nstrips, int P_req, int K_req, HpLayout& best) {
+    const int n = s->n, b = s->b, sms = s->num_sms;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    double budget = 0.80 * (double)free_b;
+    bool found = false;
+    int Pmin = P_req > 0 ? P_req : 1, Pmax = P_req > 0 ? P_req : std::min(sms, (n + 1) / 2);
+    for (int P = Pmin; P <= Pmax; ++P) {
+        int inner = n - (P - 1);
+        if (inner < P) break;
+        int qmin = inner / P;
+        int K = K_req > 0 ? K_req : std::min(sms / P, qmin);
+        if (K < 1 || K > qmin || P * K > sms) continue;
+        HpLayout L;
+        hp_fill_layout(L, n, b, P, K);
+        if (L.QP > 1024) continue;
+        double bytes = (double)nstrips * L.G * L.PK * sizeof(cplx);
+        if (bytes > budget) continue;
+        if (!found || L.PK < best.PK) { best = L; found = true; }
+    }
+    if (!found) {
+        hp_set_error("hp_precond_setup: no leaf/separator partition of n=%d, b=%d (P=%d, K=%d requested) fits "
+                     "%d strips in %.1f GB of free device memory on %d SMs", n, b, P_req, K_req, nstrips,
+                     (double)free_b / 1e9, sms);
+        return 1;
+    }
+    return 0;
+}
+
+void hp_free_strips(hp_solver* s) {
+    cudaFree(s->packets); s->packets = nullptr;
+    cudaFree(s->leaf_start); s->leaf_start = nullptr;
+    cudaFree(s->leaf_q); s->leaf_q = nullptr;
+    cudaFree(s->sep); s->sep = nullptr;
+    cudaFree(s->vbuf); s->vbuf = nullptr;
+    cudaFree(s->gparts); s->gparts = nullptr;
+    cudaFree(s->xs); s->xs = nullptr;
+    cudaFree(s->bar); s->bar = nullptr;
+    s->m_lo = 0; s->m_hi = -1; s->bytes = 0;
+}
+
+int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cudaStream_t st) {
+    const int n = s->n, b = s->b, bb = b * b;
+    hp_free_strips(s);
+    const int nstrips = m_hi - m_lo + 1;
+    HpLayout L;
+    if (hp_choose_layout(s, nstrips, P_req, K_req, L)) return 1;
+    s->lay = L;
+    const int P = L.P, ns = P - 1;
+    // leaves and separators (same arithmetic as tools/strip_model.py::partition)
+    s->leaf_start_h.assign(P, 0); s->leaf_q_h.assign(P, 0); s->sep_h.assign(std::max(ns, 1), 0);
+    {
+        long inner = n - ns;
+        int pos = 0;
+        for (int l = 0; l < P; ++l) {
+            int q = (int)((inner * (l + 1)) / P - (inner * l) / P);
+            s->leaf_start_h[l] = pos; s->leaf_q_h[l] = q;
+            pos += q;
+            if (l < P - 1) { s->sep_h[l] = pos; pos += 1; }
+        }
+    }
+    HP_CUDA(cudaMalloc(&s->leaf_start, sizeof(int) * P));
+    HP_CUDA(cudaMalloc(&s->leaf_q, sizeof(int) * P));
+    HP_CUDA(cudaMalloc(&s->sep, sizeof(int) * std::max(ns, 1)));
+    HP_CUDA(cudaMemcpyAsync(s->leaf_start, s->leaf_start_h.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
+    HP_CUDA(cudaMemcpyAsync(s->leaf_q, s->leaf_q_h.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
+    HP_CUDA(cudaMemcpyAsync(s->sep, s->sep_h.data(), sizeof(int) * std::max(ns, 1), cudaMemcpyHostToDevice, st));
+    size_t pbytes = (size_t)nstrips * L.G * L.PK * sizeof(cplx);
+    HP_CUDA(cudaMalloc(&s->packets, pbytes));
+    HP_CUDA(cudaMemsetAsync(s->packets, 0, pbytes, st));
+    HP_CUDA(cudaMalloc(&s->vbuf, sizeof(cplx) * n));
+    HP_CUDA(cudaMalloc(&s->gparts, sizeof(cplx) * L.G * 2 * b));
+    HP_CUDA(cudaMalloc(&s->xs, sizeof(cplx) * L.NSP));
+    HP_CUDA(cudaMalloc(&s->bar, sizeof(unsigned int) * 4));
+    HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int) * 4, st));
+    HP_CUDA(cudaMemsetAsync(s->status, 0, sizeof(int), st));
+    s->m_lo = m_lo; s->m_hi = m_hi;
+    s->bytes = (int64_t)pbytes;
+
+    // batch size from the scratch footprint
+    size_t per_strip = ((size_t)n * bb * 2 + (size_t)n * b + (size_t)P * bb + (size_t)9 * std::max(ns, 1) * bb) * sizeof(cplx);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    size_t cap = std::min<size_t>((size_t)(0.5 * (double)free_b), (size_t)12 << 30);
+    int LB = (int)std::max<size_t>(1, std::min<size_t>((size_t)nstrips, cap / per_strip));
+    HpSetupArgs a;
+    a.c = hp_ctx(s); a.lay = L; a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
+    a.m_lo = m_lo; a.packets = s->packets; a.status = s->status;
+    cplx* scratch = nullptr;
+    HP_CUDA(cudaMalloc(&scratch, per_strip * LB));
+    {
+        cplx* p = scratch;
+        a.Finv = p; p += (size_t)LB * n * bb;
+        a.Binv = p; p += (size_t)LB * n * bb;
+        a.gcol = p; p += (size_t)LB * n * b;
+        a.tp = p; p += (size_t)LB * P * bb;
+        size_t sz = (size_t)LB * std::max(ns, 1) * bb;
+        a.Sd = p; p += sz; a.So = p; p += sz; a.FX = p; p += sz; a.FXi = p; p += sz; a.PF = p; p += sz;
+        a.BX = p; p += sz; a.BXi = p; p += sz; a.PB = p; p += sz; a.Njj = p; p += sz;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    const int leaf_threads = ((L.QP + 31) / 32) * 32;
+    for (int m0 = m_lo; m0 <= m_hi; m0 += LB) {
+        a.m0 = m0;
+        a.nb = std::min(LB, m_hi - m0 + 1);
+        int t1 = a.nb * P * 2;
+        hp_chain_kernel<<<(t1 + 63) / 64, 64, 0, st>>>(a);
+        hp_leaf_kernel<<<a.nb * P, leaf_threads, 0, st>>>(a);
+        if (ns > 0) {
+            if (P > 2) {
+                int t3 = a.nb * P * b;
+                hp_corner_kernel<<<(t3 + 127) / 128, 128, 0, st>>>(a);
+            }
+            int t4 = a.nb * ns;
+            hp_sep_blocks_kernel<<<(t4 + 127) / 128, 128, 0, st>>>(a);
+            hp_sep_chain_kernel<<<(a.nb * 2 + 31) / 32, 32, 0, st>>>(a);
+            hp_sep_diaginv_kernel<<<(t4 + 63) / 64, 64, 0, st>>>(a);
+            int t7 = a.nb * ns * b;
+            hp_sep_rows_kernel<<<(t7 + 127) / 128, 128, 0, st>>>(a);
+        }
+        HP_CUDA(cudaGetLastError());
+    }
+    cudaEventRecord(e1, st);
+    HP_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    s->setup_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    HP_CUDA(cudaFree(scratch));
+    int status = 0;
+    HP_CUDA(cudaMemcpy(&status, s->status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status) {
+        hp_set_error("hp_precond_setup: a pivot vanished while factoring the strips (status %d)", status);
+        return 3;
+    }
+    return 0;
+}

@@ -1,0 +1,269 @@
+// The sweeps of algo2_4 (/root/reference/code.py:366-380): a chain of strip solves y = T_m v, each of which
+// depends on the previous one.  One persistent cooperative kernel walks the whole chain; per strip every
+// CTA streams its packet (csrc/hp_internal.cuh) once and the CTAs meet at two grid barriers:
+//
+//   S1  g   = Gp v_own                      (2b numbers per CTA)            -> gparts, v_own -> vbuf
+//   ---- barrier A
+//   S2  y0  = Wp v_leaf                     (own rows of the leaf product)
+//       rho = e_b v_s - sum(gparts)         (separator right-hand sides)
+//       x_S(own rows) = Np rho              (dense separator inverse)        -> xs
+//   ---- barrier B
+//   S3  y   = y0 - Gf^T x_left - Gl^T x_right, separator columns y_s = x_s[b-1]
+//       epilogue: forward   u_{m+1} -= A_{m+1,m} y                           (code.py:370)
+//                 backward  u_m <- u_m - y   (reference, :372-380 fused by linearity)  or  u_m <- y (paper)
+//       and the input of the next strip is formed in place (no barrier between S3 and the next S1).
+//
+// Only L2-resident exchange buffers cross CTAs (vbuf, gparts, xs, u); they are read with ld.global.cg.
+#include "hp_internal.cuh"
+
+#define HP_SWEEP_THREADS 256
+
+struct HpSweepArgs {
+    int n, b;
+    HpLayout lay;
+    const int *leaf_start, *leaf_q, *sep;
+    const cplx* packets;
+    int m_lo;
+    int mode, m_from, m_to, diag_mode;
+    cplx* u;
+    const cplx* vin;
+    cplx* yout;
+    cplx *vbuf, *gparts, *xs;
+    unsigned int* bar;
+    const cplx *s2t, *is1t;
+    double ih2;
+};
+
+__device__ __forceinline__ cplx ldcg(const cplx* p) {
+    double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+    return v;
+}
+
+__device__ __forceinline__ void hp_grid_barrier(unsigned int* bar, unsigned int& target, unsigned int nctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nctas;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while ((int)(v - target) < 0);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ cplx hp_warp_sum2(cplx v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    return v;
+}
+
+// coupling A_{j+1,j}[c] = c3 of grid row j+1 = s2((j+.5)h)/(h^2 s1(ih)) = A_{j,j+1}[c] (c4 of row j); rowfac is
+// the x2 part for the pair (j, j+1), 1-based j
+__device__ __forceinline__ cplx hp_rowfac(const HpSweepArgs& a, int j) { return cscale(a.ih2, a.s2t[2 * j + 1]); }
+
+extern "C" __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs a) {
+    extern __shared__ double2 smem[];
+    const int b = a.b, n = a.n, K = a.lay.K, P = a.lay.P, G = a.lay.G, QP = a.lay.QP, CW = a.lay.CW;
+    const int NS = a.lay.NS, NSP = a.lay.NSP, NR = a.lay.NR;
+    const int g = blockIdx.x, l = g / K, k = g % K;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = HP_SWEEP_THREADS / 32;
+    const int q = a.leaf_q[l], ls = a.leaf_start[l];
+    const int lc0 = (q * k) / K, lc1 = (q * (k + 1)) / K, ncols = lc1 - lc0, c0 = ls + lc0;
+    const int row0 = g * NR, nrows = max(0, min(NR, NS - row0));
+
+    cplx* v_own = smem;                 // [CW]
+    cplx* v_leaf = v_own + CW;          // [QP]
+    cplx* y0 = v_leaf + QP;             // [CW]
+    cplx* rho = y0 + CW;                // [NSP]
+    cplx* xlr = rho + NSP;              // [2b]  x_left, x_right
+    cplx* xrow = xlr + 2 * b;           // [NR+1] own rows of x_S
+
+    unsigned int target = 0;
+    const int step = a.mode == 1 ? -1 : 1;
+    const int nsteps = a.mode == 2 ? 1 : (a.mode == 0 ? a.m_to - a.m_from + 1 : a.m_from - a.m_to + 1);
+    const cplx sgn = cmake(a.diag_mode == 0 ? 1.0 : -1.0, 0.0);
+
+    // input of the first strip
+    int m = a.m_from;
+    if (tid < ncols) {
+        int c = c0 + tid;
+        cplx v;
+        if (a.mode == 2) v = a.vin[c];
+        else if (a.mode == 0) v = ldcg(a.u + (size_t)(m - 1) * n + c);
+        else {
+            v = ldcg(a.u + (size_t)(m - 1) * n + c);
+            if (m < n) {
+                cplx cp = cmul(cmul(hp_rowfac(a, m), a.is1t[2 * (c + 1)]), sgn);
+                v = cfma(cp, ldcg(a.u + (size_t)m * n + c), v);
+            }
+        }
+        v_own[tid] = v;
+    }
+    __syncthreads();
+
+    for (int it = 0; it < nsteps; ++it, m += step) {
+        const cplx* pk = a.packets + ((size_t)(m - a.m_lo) * G + g) * a.lay.PK;
+        const cplx* Wp = pk;
+        const cplx* Gp = pk + a.lay.offG;
+        const cplx* Np = pk + a.lay.offN;
+        // pull the next strip's packet towards L2 while this one is processed
+        if (it + 1 < nsteps) {
+            const char* nx = (const char*)(a.packets + ((size_t)(m + step - a.m_lo) * G + g) * a.lay.PK);
+            size_t bytes = a.lay.PK * sizeof(cplx);
+            for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)HP_SWEEP_THREADS * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+        }
+        // ---- S1
+        if (tid < ncols) a.vbuf[c0 + tid] = v_own[tid];
+        for (int kap = warp; kap < 2 * b; kap += nwarps) {
+            cplx acc = cmake(0.0, 0.0);
+            for (int cc = lane; cc < ncols; cc += 32) acc = cfma(Gp[(size_t)kap * CW + cc], v_own[cc], acc);
+            acc = hp_warp_sum2(acc);
+            if (lane == 0) a.gparts[(size_t)g * 2 * b + kap] = acc;
+        }
+        hp_grid_barrier(a.bar, target, G);
+        // ---- S2
+        for (int c = tid; c < q; c += HP_SWEEP_THREADS) v_leaf[c] = ldcg(a.vbuf + ls + c);
+        if (nrows > 0) {
+            for (int e = tid; e < NS; e += HP_SWEEP_THREADS) {
+                int j = e / b, kap = e - j * b;
+                cplx acc = cmake(0.0, 0.0);
+                for (int kk = 0; kk < K; ++kk) {
+                    acc = csub(acc, ldcg(a.gparts + ((size_t)(j * K + kk) * 2 + 1) * b + kap));        // Gl of leaf j
+                    acc = csub(acc, ldcg(a.gparts + ((size_t)((j + 1) * K + kk) * 2) * b + kap));      // Gf of leaf j+1
+                }
+                if (kap == b - 1) {
+                    int s = a.sep[j];
+                    cplx vs;
+                    if (a.mode == 2) vs = a.vin[s];
+                    else {
+                        vs = ldcg(a.u + (size_t)(m - 1) * n + s);
+                        if (a.mode == 1 && m < n) {
+                            cplx cp = cmul(cmul(hp_rowfac(a, m), a.is1t[2 * (s + 1)]), sgn);
+                            vs = cfma(cp, ldcg(a.u + (size_t)m * n + s), vs);
+                        }
+                    }
+                    acc = cadd(acc, vs);
+                }
+                rho[e] = acc;
+            }
+        }
+        __syncthreads();
+        for (int cc = warp; cc < ncols; cc += nwarps) {
+            cplx acc = cmake(0.0, 0.0);
+            const cplx* wr = Wp + (size_t)cc * QP;
+            for (int c = lane; c < q; c += 32) acc = cfma(wr[c], v_leaf[c], acc);
+            acc = hp_warp_sum2(acc);
+            if (lane == 0) y0[cc] = acc;
+        }
+        for (int rr = warp; rr < nrows; rr += nwarps) {
+            cplx acc = cmake(0.0, 0.0);
+            const cplx* nr = Np + (size_t)rr * NSP;
+            for (int e = lane; e < NS; e += 32) acc = cfma(nr[e], rho[e], acc);
+            acc = hp_warp_sum2(acc);
+            if (lane == 0) { a.xs[row0 + rr] = acc; xrow[rr] = acc; }
+        }
+        hp_grid_barrier(a.bar, target, G);
+        // ---- S3
+        if (tid < 2 * b) {
+            int side = tid / b, kap = tid - side * b;
+            int j = l - 1 + side;
+            xlr[tid] = (j >= 0 && j < P - 1) ? ldcg(a.xs + (size_t)j * b + kap) : cmake(0.0, 0.0);
+        }
+        __syncthreads();
+        const int mn = m + step;               // next strip
+        const bool more = it + 1 < nsteps;
+        if (tid < ncols) {
+            int c = c0 + tid;
+            cplx y = y0[tid];
+            for (int kap = 0; kap < 2 * b; ++kap) y = cfms(Gp[(size_t)kap * CW + tid], xlr[kap], y);
+            if (a.mode == 2) {
+                a.yout[c] = y;
+            } else if (a.mode == 0) {
+                // u_{m+1} -= c3(row m+1) y ; the result is the input of strip m+1
+                cplx cp = cmul(hp_rowfac(a, m), a.is1t[2 * (c + 1)]);
+                cplx un = cfms(cp, y, ldcg(a.u + (size_t)m * n + c));
+                a.u[(size_t)m * n + c] = un;
+                v_own[tid] = un;
+            } else {
+                cplx un = a.diag_mode == 0 ? csub(ldcg(a.u + (size_t)(m - 1) * n + c), y) : y;
+                a.u[(size_t)(m - 1) * n + c] = un;
+                if (more) {
+                    // input of strip m-1: u_{m-1} (+/-) c4(row m-1) u_m
+                    cplx cp = cmul(cmul(hp_rowfac(a, mn), a.is1t[2 * (c + 1)]), sgn);
+                    v_own[tid] = cfma(cp, un, ldcg(a.u + (size_t)(mn - 1) * n + c));
+                }
+            }
+        }
+        // separator columns: the CTA that computed row (j, b-1) of x_S owns the update of column sep[j]
+        if (tid < nrows) {
+            int row = row0 + tid;
+            int j = row / b, kap = row - j * b;
+            if (kap == b - 1) {
+                int s = a.sep[j];
+                cplx y = xrow[tid];
+                if (a.mode == 2) a.yout[s] = y;
+                else if (a.mode == 0) {
+                    cplx cp = cmul(hp_rowfac(a, m), a.is1t[2 * (s + 1)]);
+                    a.u[(size_t)m * n + s] = cfms(cp, y, ldcg(a.u + (size_t)m * n + s));
+                } else {
+                    a.u[(size_t)(m - 1) * n + s] = a.diag_mode == 0 ? csub(ldcg(a.u + (size_t)(m - 1) * n + s), y) : y;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout, int m_from, int m_to,
+                    int diag_mode, cudaStream_t st) {
+    if (!s->packets) { hp_set_error("sweep: preconditioner not set up"); return 1; }
+    int lo = mode == 1 ? m_to : m_from, hi = mode == 1 ? m_from : m_to;
+    if (mode == 2) lo = hi = m_from;
+    if (lo > hi) return 0;
+    if (lo < s->m_lo || hi > s->m_hi) {
+        hp_set_error("sweep: strips %d..%d requested, solver holds %d..%d", lo, hi, s->m_lo, s->m_hi);
+        return 1;
+    }
+    HpSweepArgs a;
+    a.n = s->n; a.b = s->b; a.lay = s->lay;
+    a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
+    a.packets = s->packets; a.m_lo = s->m_lo;
+    a.mode = mode; a.m_from = m_from; a.m_to = m_to; a.diag_mode = diag_mode;
+    a.u = u; a.vin = vin; a.yout = yout;
+    a.vbuf = s->vbuf; a.gparts = s->gparts; a.xs = s->xs; a.bar = s->bar;
+    a.s2t = s->s2t; a.is1t = s->is1t;
+    a.ih2 = 1.0 / (s->pml.h * s->pml.h);
+    const HpLayout& L = s->lay;
+    size_t smem = sizeof(cplx) * ((size_t)2 * L.CW + L.QP + L.NSP + 2 * s->b + L.NR + 1);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        HP_CUDA(cudaFuncSetAttribute(hp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int), st));
+    void* args[] = {&a};
+    HP_CUDA(cudaLaunchCooperativeKernel((const void*)hp_sweep_kernel, dim3(L.G), dim3(HP_SWEEP_THREADS), args, smem, st));
+    return 0;
+}
+
+extern "C" int hp_sweep_forward(hp_solver* s, double* u_dev, int m_from, int m_to, void* stream) {
+    if (!s) { hp_set_error("hp_sweep_forward: null solver"); return 1; }
+    return hp_sweep_launch(s, 0, (cplx*)u_dev, nullptr, nullptr, m_from, m_to, 0, (cudaStream_t)stream);
+}
+
+extern "C" int hp_sweep_backward(hp_solver* s, double* u_dev, int m_from, int m_to, int diag_mode, void* stream) {
+    if (!s) { hp_set_error("hp_sweep_backward: null solver"); return 1; }
+    return hp_sweep_launch(s, 1, (cplx*)u_dev, nullptr, nullptr, m_from, m_to, diag_mode, (cudaStream_t)stream);
+}
+
+extern "C" int hp_strip_apply(hp_solver* s, int m, const double* v_dev, double* y_dev, void* stream) {
+    if (!s) { hp_set_error("hp_strip_apply: null solver"); return 1; }
+    return hp_sweep_launch(s, 2, nullptr, (const cplx*)v_dev, (cplx*)y_dev, m, m, 0, (cudaStream_t)stream);
+}

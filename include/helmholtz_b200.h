@@ -44,6 +44,10 @@ int64_t hp_csr_nnz(int n);
 int hp_assemble_csr(hp_solver* s, int32_t* indptr_dev, int32_t* indices_dev, double* data_dev, void* stream);
 /* y = A x without forming A (the matvec scipy's gmres performs at code.py:516, iterative.py `matvec`) */
 int hp_stencil_matvec(hp_solver* s, const double* x_dev, double* y_dev, void* stream);
+/* the same for the grid rows j_lo <= j < j_hi (0-based) of a slab: x_dev/y_dev hold those rows only, x_south_dev /
+ * x_north_dev are the halo rows j_lo-1 and j_hi received from the neighbouring ranks (NULL on the grid boundary) */
+int hp_stencil_matvec_rows(hp_solver* s, int j_lo, int j_hi, const double* x_dev, const double* x_south_dev,
+                           const double* x_north_dev, double* y_dev, void* stream);
 /* y = A x from the assembled CSR arrays */
 int hp_csr_matvec(int64_t nrows, const int32_t* indptr_dev, const int32_t* indices_dev, const double* data_dev,
                   const double* x_dev, double* y_dev, void* stream);
@@ -51,11 +55,13 @@ int hp_csr_matvec(int64_t nrows, const int32_t* indptr_dev, const int32_t* indic
 /* ---- preconditioner ------------------------------------------------------------------------------ */
 
 /* algo2_3 (code.py:345-353): factor the front block H_F and every moving-PML strip H_m, m = m_lo..m_hi
- * (b+1 <= m_lo <= m_hi <= n; pass 0,0 for all).  qmax (<= 64, 0 = default 64) bounds the leaf width of the
- * x1 partition.  Strips outside [m_lo, m_hi] belong to other ranks of a slab decomposition. */
-int hp_precond_setup(hp_solver* s, int qmax, int m_lo, int m_hi, void* stream);
-/* bytes of device memory held by the factorisation */
+ * (b+1 <= m_lo, m_hi <= n; pass 0,0 for all; m_lo > m_hi = front block only).  Strips outside [m_lo, m_hi]
+ * belong to other ranks of a slab decomposition.  P, K choose the x1 partition of the strips (P leaves
+ * separated by P-1 separator columns, K CTAs per leaf, P*K <= number of SMs); 0,0 = chosen automatically. */
+int hp_precond_setup(hp_solver* s, int P, int K, int m_lo, int m_hi, void* stream);
+/* bytes of device memory held by the strip factorisation, and the device time the last setup took */
 int64_t hp_precond_bytes(hp_solver* s);
+double hp_precond_setup_ms(hp_solver* s);
 
 /* The three stages of algo2_4 (code.py:356-385), operating in place on the field u_dev (n*n complex):
  *   hp_front_begin   : T_F u_F = H_F^{-1} u_F kept aside, u_{b+1} -= A_{b+1,F} T_F u_F        (:364-365)
@@ -73,9 +79,11 @@ int hp_front_end(hp_solver* s, double* u_dev, void* stream);
 int hp_precond_apply(hp_solver* s, const double* f_dev, double* u_dev, int diag_mode, void* stream);
 /* y = T_m v : last n entries of H_m^{-1} [0; v]  (lu_Hm_ra[m-b-1].solve(u_temp)[-n:], code.py:370) */
 int hp_strip_apply(hp_solver* s, int m, const double* v_dev, double* y_dev, void* stream);
-/* copies of one strip's generators to host arrays (test hook): W[P*QP*QP], G[P*2*b*QP], nodes[(P-1)*12*b*b] */
-int hp_strip_layout(hp_solver* s, int* d, int* P, int* QP, int* leaf_start_host /* P+1, may be NULL */);
-int hp_strip_generators(hp_solver* s, int m, double* W_host, double* G_host, double* nodes_host);
+/* test hooks: the partition in use, and a host copy of one strip's packed generators
+ * (G = P*K packets of PK complex numbers; layout in csrc/hp_internal.cuh) */
+int hp_strip_layout(hp_solver* s, int* P, int* K, int* QP, int* CW, int* NS, int* NR, int64_t* PK,
+                    int* leaf_start_host /* P */, int* leaf_q_host /* P */, int* sep_host /* P-1 */);
+int hp_strip_packets(hp_solver* s, int m, double* packets_host);
 
 /* ---- Krylov vector kernels (scipy gmres inner loop, iterative.py; called from code.py:516) -------- */
 

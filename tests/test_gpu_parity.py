@@ -1,0 +1,181 @@
+"""Parity of the CUDA path (through the C ABI / the host mirror of the reference API) against the oracle and
+against the golden vectors of the unmodified reference.  Runs on the B200 box: pytest -m gpu."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import helmholtz_oracle as orc  # noqa: E402
+from tools import strip_model as sm  # noqa: E402
+
+CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")))
+IDS = [os.path.basename(p)[:-4] for p in CASES]
+
+
+@pytest.fixture(scope="module")
+def hp():
+    import helmholtz_preconditioner_b200 as hp
+    hp.load()
+    assert torch.cuda.is_available(), "the gpu tests need a CUDA device"
+    return hp
+
+
+def _load(path):
+    g = np.load(path, allow_pickle=False)
+    n, b = int(g["n"]), int(g["b"])
+    omega = 2 * np.pi * float(g["wave_num"]) + 1j * float(g["alpha"])
+    h = 1 / (n + 1)
+    return g, dict(b=b, const=float(g["const"]), eta=b * h, omega=omega, h=h, n=n)
+
+
+def relerr(a, b):
+    a = a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return np.linalg.norm(a.ravel() - np.asarray(b).ravel()) / np.linalg.norm(np.asarray(b).ravel())
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.complex128))).cuda()
+
+
+@pytest.mark.parametrize("path", CASES, ids=IDS)
+def test_assembly_golden(hp, path):
+    """build_A_matrix: sparsity pattern bit exact, values to 1e-12 (code.py:202-219)."""
+    g, p = _load(path)
+    A = hp.build_A_matrix(c_mat=g["c_mat"], **p)
+    indptr, indices, data = A.to_host()
+    assert np.array_equal(indptr, g["A_indptr"])
+    assert np.array_equal(indices, g["A_indices"])
+    assert np.max(np.abs(data - g["A_data"]) / np.abs(g["A_data"])) < 1e-12
+    y = A @ g["x_rand"]
+    assert relerr(y, g["A_x_rand"]) < 1e-13
+    y2 = A.solver.matvec(dev(g["x_rand"]))
+    assert relerr(y2, g["A_x_rand"]) < 1e-13
+
+
+@pytest.mark.parametrize("n,b,P,K", [(45, 12, 4, 2), (63, 12, 5, 3), (40, 5, 1, 3), (40, 5, 7, 1), (50, 20, 3, 4)])
+def test_strip_generators_vs_model(hp, n, b, P, K):
+    """The packets written by the setup kernels against the numpy model of the same layout."""
+    omega = 2 * np.pi * 5 + 2j
+    c_mat = orc.init_c1_f1(omega, n)[0]
+    s = hp.HelmholtzSolver(n, b, omega, 60.0, c_mat)
+    s.setup_preconditioner(P=P, K=K)
+    h = 1 / (n + 1)
+    for m in (b + 1, (n + b) // 2, n):
+        L, pk = s.strip_packets(m)
+        assert (L["P"], L["K"]) == (P, K)
+        mod = sm.StripModel(m, b, 60.0, b * h, omega, h, n, c_mat, P=P, K=K)
+        pt = mod.part
+        assert np.array_equal(L["leaf_start"], pt["leaf_start"]) and np.array_equal(L["q"], pt["q"])
+        QP, CW, NS, NR = L["QP"], L["CW"], L["NS"], L["NR"]
+        for l in range(P):
+            q = int(pt["q"][l])
+            for k in range(K):
+                g_ = l * K + k
+                lc0, lc1 = (q * k) // K, (q * (k + 1)) // K
+                Wp = pk[g_, :CW * QP].reshape(CW, QP)
+                Gp = pk[g_, CW * QP:CW * QP + 2 * b * CW].reshape(2 * b, CW)
+                assert np.allclose(Wp[:lc1 - lc0, :q], mod.W[l, lc0:lc1, :q], rtol=0, atol=1e-11 * np.abs(mod.W).max())
+                Gm = mod.G[l].reshape(2 * b, -1)[:, lc0:lc1]
+                assert np.allclose(Gp[:, :lc1 - lc0], Gm, rtol=0, atol=1e-11 * max(np.abs(mod.G).max(), 1e-300))
+        if NS:
+            offN = CW * QP + 2 * b * CW
+            N = np.zeros((NS, NS), complex)
+            for row in range(NS):
+                N[row] = pk[row // NR, offN + (row % NR) * NS: offN + (row % NR + 1) * NS]
+            assert np.allclose(N, mod.N, rtol=0, atol=1e-11 * np.abs(mod.N).max())
+    s.close()
+
+
+@pytest.mark.parametrize("n,b,P,K", [(63, 12, 5, 3), (40, 5, 1, 3), (40, 5, 7, 1), (200, 12, 0, 0), (130, 20, 6, 5)])
+def test_strip_apply_vs_oracle(hp, n, b, P, K):
+    """y = T_m v against the oracle's splu solve (code.py:368-370)."""
+    omega = 2 * np.pi * (n / 10) + 2j
+    c_mat = orc.init_c1_f1(omega, n)[0]
+    h = 1 / (n + 1)
+    Pc = orc.SweepingPreconditioner(b, 60.0, b * h, omega, h, n, c_mat)
+    s = hp.HelmholtzSolver(n, b, omega, 60.0, c_mat).setup_preconditioner(P=P, K=K)
+    rng = np.random.default_rng(3)
+    for m in (b + 1, (n + b) // 2, n - 1, n):
+        v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        y = s.strip_apply(m, dev(v))
+        assert relerr(y, Pc.T(m, v)) < 1e-12
+    s.close()
+
+
+GM = [p for p in CASES if "M_f" in np.load(p).files]
+GM_IDS = [os.path.basename(p)[:-4] for p in GM]
+
+
+@pytest.mark.parametrize("path", GM, ids=GM_IDS)
+def test_preconditioner_golden(hp, path):
+    """algo2_4 against the reference's own output (code.py:356-385)."""
+    g, p = _load(path)
+    s, _ = hp.algo2_3(c_mat=g["c_mat"], **p)
+    n, b = p["n"], p["b"]
+    u = hp.algo2_4(g["f_mat"].flatten(), b, n, s)
+    assert relerr(u, g["M_f"]) < 1e-12
+    u = hp.algo2_4(g["x_rand"], b, n, s)
+    assert relerr(u, g["M_x_rand"]) < 1e-12
+    m = int(g["Hm_mid_m"])
+    assert relerr(s.strip_apply(m, dev(g["x_rand"][:n])), g["T_mid_v"]) < 1e-12
+    # Engquist-Ying form of the diagonal solve, against the oracle
+    Pp = orc.SweepingPreconditioner(c_mat=g["c_mat"], diag="paper", **p)
+    assert relerr(hp.algo2_4(g["x_rand"], b, n, s, diag="paper"), Pp.apply(g["x_rand"])) < 1e-12
+    s.close()
+
+
+@pytest.mark.parametrize("path", GM, ids=GM_IDS)
+def test_gmres_golden(hp, path):
+    """run_solver: the literal reference (M ignores its argument) and the well-defined variant (M applied to
+    the vector), iteration counts and residual histories against the reference's."""
+    g, p = _load(path)
+    args = (p["n"], p["b"], float(g["wave_num"]), p["const"], float(g["alpha"]), getattr(hp, str(g["init"])))
+    r = hp.run_solver(*args, precond_input="vector", maxiter=25, verbose=False)
+    assert r.niter == len(g["gmres_vector_hist"]) and r.info == int(g["gmres_vector_info"])
+    assert np.allclose(r.residuals, g["gmres_vector_hist"], rtol=1e-8, atol=0)
+    assert relerr(r.u, g["gmres_vector_u"]) < 1e-8
+    r = hp.run_solver(*args, verbose=False)
+    assert abs(r.niter - len(g["gmres_literal_hist"])) <= 2 and 1 <= r.niter <= 3
+    assert r.info == int(g["gmres_literal_info"])
+    assert r.residuals[-1] < 1e-12
+
+
+def test_krylov_kernels(hp):
+    from helmholtz_preconditioner_b200.gmres import DeviceVectors
+    rng = np.random.default_rng(5)
+    N, k = 100003, 7
+    V = rng.standard_normal((k, N)) + 1j * rng.standard_normal((k, N))
+    w = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    vec = DeviceVectors(N, torch.device("cuda:0"))
+    Vd, wd = dev(V).reshape(k, N), dev(w)
+    assert abs(vec.norm(wd) - np.linalg.norm(w)) < 1e-12 * np.linalg.norm(w)
+    h, h1, h0 = vec.mgs(Vd, k, wd)
+    wr = w.copy()
+    hr = np.zeros(k, complex)
+    for j in range(k):
+        hr[j] = np.vdot(V[j], wr)
+        wr -= hr[j] * V[j]
+    assert np.allclose(h, hr, rtol=1e-12) and abs(h1 - np.linalg.norm(wr)) < 1e-11 * h1
+    assert abs(h0 - np.linalg.norm(w)) < 1e-12 * h0
+    assert relerr(wd, wr) < 1e-13
+    x = dev(w)
+    y = rng.standard_normal(k) + 1j * rng.standard_normal(k)
+    vec.combine(Vd, y, x)
+    assert relerr(x, w + y @ V) < 1e-13
+
+
+def test_medium_preconditioner_vs_oracle(hp):
+    """n = 255 (the reference's second problem size, code.py:579), automatic partition."""
+    n, b, wn, const = 255, 12, 32, 62
+    omega = 2 * np.pi * wn + 2j
+    h = 1 / (n + 1)
+    c_mat, f_mat = orc.init_c1_f1(omega, n)
+    Pc = orc.SweepingPreconditioner(b, const, b * h, omega, h, n, c_mat)
+    s, _ = hp.algo2_3(b, const, b * h, omega, h, n, c_mat)
+    f = f_mat.flatten().astype(np.complex128)
+    assert relerr(hp.algo2_4(f, b, n, s), Pc.apply(f)) < 1e-12
+    s.close()
