@@ -17,6 +17,9 @@ SIGNATURES = {
     "hp_last_error": (C.c_char_p, []),
     "hp_version": (_i, []),
     "hp_device_ok": (_i, []),
+    "hp_launch_count": (_i64, []),
+    "hp_profile_enable": (_i, [_vp, _i]),
+    "hp_profile_read": (_i, [_vp, C.POINTER(_d), _ip, C.POINTER(_i64)]),
     "hp_create": (_i, [C.POINTER(_vp), _i, _i, _d, _d, _d, _vp, _i, _vp]),
     "hp_destroy": (_i, [_vp]),
     "hp_csr_nnz": (_i64, [_i]),

@@ -14,6 +14,46 @@ void hp_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* hp_last_error(void) { return g_err; }
+
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void hp_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t hp_launch_count(void) { return (int64_t)g_launches.load(); }
+
+void hp_profile_begin(hp_solver* s, cudaStream_t st) {
+    if (!s->prof_on) return;
+    if (s->prof_used + 2 > (int)s->prof_ev.size()) {
+        for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); s->prof_ev.push_back(e); }
+    }
+    cudaEventRecord(s->prof_ev[s->prof_used], st);
+}
+void hp_profile_end(hp_solver* s, cudaStream_t st, int64_t bytes) {
+    if (!s->prof_on) return;
+    cudaEventRecord(s->prof_ev[s->prof_used + 1], st);
+    s->prof_used += 2;
+    s->prof_bytes += bytes;
+}
+extern "C" int hp_profile_enable(hp_solver* s, int on) {
+    if (!s) return 1;
+    s->prof_on = on; s->prof_used = 0; s->prof_bytes = 0;
+    return 0;
+}
+// total device time (ms) of the sweep kernel launches since hp_profile_enable, their number and the
+// algorithmic bytes they streamed; synchronises the device
+extern "C" int hp_profile_read(hp_solver* s, double* sweep_ms, int* launches, int64_t* bytes) {
+    if (!s) return 1;
+    HP_CUDA(cudaDeviceSynchronize());
+    double tot = 0.0;
+    for (int i = 0; i + 1 < s->prof_used; i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->prof_ev[i], s->prof_ev[i + 1]);
+        tot += ms;
+    }
+    if (sweep_ms) *sweep_ms = tot;
+    if (launches) *launches = s->prof_used / 2;
+    if (bytes) *bytes = s->prof_bytes;
+    return 0;
+}
 extern "C" int hp_version(void) { return 100; }
 
 extern "C" int hp_device_ok(void) {
@@ -64,6 +104,7 @@ extern "C" int hp_destroy(hp_solver* s) {
     cudaFree(s->s1t); cudaFree(s->is1t); cudaFree(s->s2t); cudaFree(s->is2t);
     cudaFree(s->c_mat); cudaFree(s->kappa); cudaFree(s->status);
     cudaFree(s->f_low); cudaFree(s->f_invd); cudaFree(s->f_up); cudaFree(s->TF);
+    for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     delete s;
     return 0;
 }

@@ -37,9 +37,9 @@ __global__ void hp_kappa_kernel(int n, const double* __restrict__ c_mat, double*
 
 int hp_launch_tables(hp_solver* s, cudaStream_t st) {
     int n = s->n, len = 2 * n + 3;
-    hp_tables_kernel<<<(len + 127) / 128, 128, 0, st>>>(n, s->pml, s->s1t, s->is1t, s->s2t, s->is2t);
+    hp_count_launch(); hp_tables_kernel<<<(len + 127) / 128, 128, 0, st>>>(n, s->pml, s->s1t, s->is1t, s->s2t, s->is2t);
     dim3 blk(32, 8), grd((n + 31) / 32, (n + 31) / 32);
-    hp_kappa_kernel<<<grd, blk, 0, st>>>(n, s->c_mat, s->kappa);
+    hp_count_launch(); hp_kappa_kernel<<<grd, blk, 0, st>>>(n, s->c_mat, s->kappa);
     HP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -168,7 +168,7 @@ extern "C" int hp_assemble_csr(hp_solver* s, int32_t* indptr, int32_t* indices, 
     if (hp_csr_nnz(s->n) > 2147483647LL) { hp_set_error("hp_assemble_csr: nnz exceeds int32 indices"); return 1; }
     int64_t N = (int64_t)s->n * s->n;
     double ih2 = 1.0 / (s->pml.h * s->pml.h);
-    hp_assemble_csr_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    hp_count_launch(); hp_assemble_csr_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         s->n, ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa, indptr, indices, (cplx*)data);
     HP_CUDA(cudaGetLastError());
     return 0;
@@ -180,7 +180,7 @@ extern "C" int hp_stencil_matvec_rows(hp_solver* s, int j_lo, int j_hi, const do
     if (j_lo < 0 || j_hi > s->n || j_lo >= j_hi) { hp_set_error("hp_stencil_matvec_rows: bad row range %d..%d", j_lo, j_hi); return 1; }
     double ih2 = 1.0 / (s->pml.h * s->pml.h);
     dim3 grd((s->n + 127) / 128, (j_hi - j_lo + HP_SPMV_ROWS - 1) / HP_SPMV_ROWS);
-    hp_stencil_matvec_kernel<<<grd, 128, 0, (cudaStream_t)stream>>>(
+    hp_count_launch(); hp_stencil_matvec_kernel<<<grd, 128, 0, (cudaStream_t)stream>>>(
         s->n, j_lo, j_hi, ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa, (const cplx*)x,
         (const cplx*)x_south, (const cplx*)x_north, (cplx*)y);
     HP_CUDA(cudaGetLastError());
@@ -194,7 +194,7 @@ extern "C" int hp_stencil_matvec(hp_solver* s, const double* x, double* y, void*
 
 extern "C" int hp_csr_matvec(int64_t nrows, const int32_t* indptr, const int32_t* indices, const double* data,
                              const double* x, double* y, void* stream) {
-    hp_csr_matvec_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    hp_count_launch(); hp_csr_matvec_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         nrows, indptr, indices, (const cplx*)data, (const cplx*)x, (cplx*)y);
     HP_CUDA(cudaGetLastError());
     return 0;

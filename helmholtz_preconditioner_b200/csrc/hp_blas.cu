@@ -122,7 +122,7 @@ static unsigned hp_ew_grid(int64_t n) {
 
 extern "C" int hp_dotc(int64_t n, const double* x, const double* y, double* out, void* stream) {
     if (hp_red_scratch()) return 2;
-    hp_reduce_kernel<0><<<hp_red_grid(n), HP_RED_THREADS, 0, (cudaStream_t)stream>>>(
+    hp_count_launch(); hp_reduce_kernel<0><<<hp_red_grid(n), HP_RED_THREADS, 0, (cudaStream_t)stream>>>(
         n, (const cplx*)x, (const cplx*)y, g_partials, g_ticket, (cplx*)out);
     HP_CUDA(cudaGetLastError());
     return 0;
@@ -130,20 +130,20 @@ extern "C" int hp_dotc(int64_t n, const double* x, const double* y, double* out,
 
 extern "C" int hp_nrm2(int64_t n, const double* x, double* out, void* stream) {
     if (hp_red_scratch()) return 2;
-    hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, (cudaStream_t)stream>>>(
+    hp_count_launch(); hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, (cudaStream_t)stream>>>(
         n, (const cplx*)x, (const cplx*)x, g_partials, g_ticket, (cplx*)out);
     HP_CUDA(cudaGetLastError());
     return 0;
 }
 
 extern "C" int hp_axpy(int64_t n, double a_re, double a_im, const double* x, double* y, void* stream) {
-    hp_axpy_kernel<<<hp_ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, cmake(a_re, a_im), (const cplx*)x, (cplx*)y);
+    hp_count_launch(); hp_axpy_kernel<<<hp_ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, cmake(a_re, a_im), (const cplx*)x, (cplx*)y);
     HP_CUDA(cudaGetLastError());
     return 0;
 }
 
 extern "C" int hp_scale_copy(int64_t n, double a_re, double a_im, const double* x, double* y, void* stream) {
-    hp_scale_copy_kernel<<<hp_ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, cmake(a_re, a_im), (const cplx*)x, (cplx*)y);
+    hp_count_launch(); hp_scale_copy_kernel<<<hp_ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, cmake(a_re, a_im), (const cplx*)x, (cplx*)y);
     HP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -153,14 +153,14 @@ extern "C" int hp_mgs(int64_t n, int k, const double* V, int64_t ldv, double* w,
     cudaStream_t st = (cudaStream_t)stream;
     cplx* h = (cplx*)hcol;
     const cplx* Vc = (const cplx*)V;
-    hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, (const cplx*)w, (const cplx*)w, g_partials,
+    hp_count_launch(); hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, (const cplx*)w, (const cplx*)w, g_partials,
                                                                   g_ticket, h + k + 1);       // h0
     for (int j = 0; j < k; ++j) {
-        hp_reduce_kernel<0><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, Vc + (size_t)j * ldv, (const cplx*)w,
+        hp_count_launch(); hp_reduce_kernel<0><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, Vc + (size_t)j * ldv, (const cplx*)w,
                                                                       g_partials, g_ticket, h + j);
-        hp_axpy_dev_kernel<<<hp_ew_grid(n), 256, 0, st>>>(n, h + j, -1.0, Vc + (size_t)j * ldv, (cplx*)w);
+        hp_count_launch(); hp_axpy_dev_kernel<<<hp_ew_grid(n), 256, 0, st>>>(n, h + j, -1.0, Vc + (size_t)j * ldv, (cplx*)w);
     }
-    hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, (const cplx*)w, (const cplx*)w, g_partials,
+    hp_count_launch(); hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, (const cplx*)w, (const cplx*)w, g_partials,
                                                                   g_ticket, h + k);           // h1
     HP_CUDA(cudaGetLastError());
     return 0;
@@ -173,7 +173,7 @@ extern "C" int hp_combine(int64_t n, int k, const double* V, int64_t ldv, const 
         int kk = k - j0 < HP_COMBINE_MAX ? k - j0 : HP_COMBINE_MAX;
         HpCombineArgs a;
         for (int j = 0; j < kk; ++j) a.y[j] = cmake(y_host[2 * (j0 + j)], y_host[2 * (j0 + j) + 1]);
-        hp_combine_kernel<<<hp_ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, kk, Vc + (size_t)j0 * ldv, ldv, a,
+        hp_count_launch(); hp_combine_kernel<<<hp_ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, kk, Vc + (size_t)j0 * ldv, ldv, a,
                                                                           (cplx*)x);
     }
     HP_CUDA(cudaGetLastError());

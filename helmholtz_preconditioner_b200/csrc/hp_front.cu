@@ -85,7 +85,7 @@ int hp_front_setup(hp_solver* s, cudaStream_t st) {
         HP_CUDA(cudaMalloc(&s->TF, sz + sizeof(cplx) * (size_t)s->b * s->n));   // TF followed by the work rows
     }
     double ih2 = 1.0 / (s->pml.h * s->pml.h);
-    hp_front_factor_kernel<<<1, 32, 0, st>>>(s->n, s->b, ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa,
+    hp_count_launch(); hp_front_factor_kernel<<<1, 32, 0, st>>>(s->n, s->b, ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa,
                                              s->f_low, s->f_invd, s->f_up, s->status);
     HP_CUDA(cudaGetLastError());
     return 0;
@@ -97,13 +97,13 @@ extern "C" int hp_front_begin(hp_solver* s, double* u_dev, void* stream) {
     const int n = s->n, b = s->b;
     cplx* u = (cplx*)u_dev;
     cplx* work = s->TF + (size_t)b * n;
-    hp_front_solve_kernel<<<1, 32, 0, st>>>(n, b, 0, b, 0, s->f_low, s->f_invd, s->f_up, u, s->TF, nullptr,
+    hp_count_launch(); hp_front_solve_kernel<<<1, 32, 0, st>>>(n, b, 0, b, 0, s->f_low, s->f_invd, s->f_up, u, s->TF, nullptr,
                                             cmake(0, 0), s->is1t, work);
     if (b < n) {
         // u_{b+1} -= A_{b+1,b} (T_F u_F)_b : A_{b+1,b} = diag(c3) of grid row b+1 (code.py:145-154, :365)
         double ih2 = 1.0 / (s->pml.h * s->pml.h);
         cplx fac = cscale(ih2, s->s2t_h[2 * (b + 1) - 1]);
-        hp_row_couple_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, fac, s->is1t, s->TF + (size_t)(b - 1) * n,
+        hp_count_launch(); hp_row_couple_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, fac, s->is1t, s->TF + (size_t)(b - 1) * n,
                                                               u + (size_t)b * n);
     }
     HP_CUDA(cudaGetLastError());
@@ -121,7 +121,7 @@ extern "C" int hp_front_end(hp_solver* s, double* u_dev, void* stream) {
         // u_b = (T_F u_F)_b - Tri_b^{-1} (A_{b,b+1} u_{b+1}) : A_{b,b+1} = diag(c4) of grid row b (code.py:131-140)
         double ih2 = 1.0 / (s->pml.h * s->pml.h);
         cplx fac = cscale(ih2, s->s2t_h[2 * b + 1]);
-        hp_front_solve_kernel<<<1, 32, 0, st>>>(n, b, b - 1, 1, 1, s->f_low, s->f_invd, s->f_up, u + (size_t)b * n,
+        hp_count_launch(); hp_front_solve_kernel<<<1, 32, 0, st>>>(n, b, b - 1, 1, 1, s->f_low, s->f_invd, s->f_up, u + (size_t)b * n,
                                                 u + (size_t)(b - 1) * n, s->TF + (size_t)(b - 1) * n, fac, s->is1t,
                                                 work);
     } else {

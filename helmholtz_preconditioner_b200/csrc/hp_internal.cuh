@@ -10,6 +10,10 @@
 #include "../../include/helmholtz_b200.h"
 
 void hp_set_error(const char* fmt, ...);
+void hp_count_launch();                       // every kernel launch of the library is counted (hp_launch_count)
+struct hp_solver;
+void hp_profile_begin(hp_solver* s, cudaStream_t st);   // CUDA-event bracket around the sweep kernel
+void hp_profile_end(hp_solver* s, cudaStream_t st, int64_t bytes);
 
 #define HP_CUDA(call)                                                                              \
     do {                                                                                           \
@@ -62,6 +66,11 @@ struct hp_solver {
     cplx *vbuf = nullptr, *gparts = nullptr, *xs = nullptr;
     unsigned int* bar = nullptr;
     int* status = nullptr;        // device flag: non-zero when a pivot vanished during setup
+    // optional CUDA-event timing of the sweep launches (hp_profile_enable / hp_profile_read)
+    int prof_on = 0;
+    std::vector<cudaEvent_t> prof_ev;   // pairs
+    int prof_used = 0;
+    int64_t prof_bytes = 0;
 };
 
 static inline HpStripCtx hp_ctx(const hp_solver* s) {

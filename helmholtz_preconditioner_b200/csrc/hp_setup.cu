@@ -248,19 +248,19 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
         a.m0 = m0;
         a.nb = std::min(LB, m_hi - m0 + 1);
         int t1 = a.nb * P * 2;
-        hp_chain_kernel<<<(t1 + 63) / 64, 64, 0, st>>>(a);
-        hp_leaf_kernel<<<a.nb * P, leaf_threads, 0, st>>>(a);
+        hp_count_launch(); hp_chain_kernel<<<(t1 + 63) / 64, 64, 0, st>>>(a);
+        hp_count_launch(); hp_leaf_kernel<<<a.nb * P, leaf_threads, 0, st>>>(a);
         if (ns > 0) {
             if (P > 2) {
                 int t3 = a.nb * P * b;
-                hp_corner_kernel<<<(t3 + 127) / 128, 128, 0, st>>>(a);
+                hp_count_launch(); hp_corner_kernel<<<(t3 + 127) / 128, 128, 0, st>>>(a);
             }
             int t4 = a.nb * ns;
-            hp_sep_blocks_kernel<<<(t4 + 127) / 128, 128, 0, st>>>(a);
-            hp_sep_chain_kernel<<<(a.nb * 2 + 31) / 32, 32, 0, st>>>(a);
-            hp_sep_diaginv_kernel<<<(t4 + 63) / 64, 64, 0, st>>>(a);
+            hp_count_launch(); hp_sep_blocks_kernel<<<(t4 + 127) / 128, 128, 0, st>>>(a);
+            hp_count_launch(); hp_sep_chain_kernel<<<(a.nb * 2 + 31) / 32, 32, 0, st>>>(a);
+            hp_count_launch(); hp_sep_diaginv_kernel<<<(t4 + 63) / 64, 64, 0, st>>>(a);
             int t7 = a.nb * ns * b;
-            hp_sep_rows_kernel<<<(t7 + 127) / 128, 128, 0, st>>>(a);
+            hp_count_launch(); hp_sep_rows_kernel<<<(t7 + 127) / 128, 128, 0, st>>>(a);
         }
         HP_CUDA(cudaGetLastError());
     }

@@ -249,7 +249,10 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     }
     HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int), st));
     void* args[] = {&a};
+    hp_count_launch();
+    hp_profile_begin(s, st);
     HP_CUDA(cudaLaunchCooperativeKernel((const void*)hp_sweep_kernel, dim3(L.G), dim3(HP_SWEEP_THREADS), args, smem, st));
+    hp_profile_end(s, st, (int64_t)(hi - lo + 1) * ((int64_t)L.G * L.PK + 3 * (int64_t)s->n) * (int64_t)sizeof(cplx));
     return 0;
 }
 

@@ -26,6 +26,12 @@ const char* hp_last_error(void);
 /* library/ABI version, and 1 if a usable CUDA device is present */
 int hp_version(void);
 int hp_device_ok(void);
+/* number of kernel launches the library has made in this process (bench.py's gpu_launches) */
+int64_t hp_launch_count(void);
+/* CUDA-event timing of the sweep kernel launches (the dominant kernel): enable/reset, then read the summed
+ * device time in ms, the number of launches and the algorithmic bytes they streamed (synchronises) */
+int hp_profile_enable(hp_solver* s, int on);
+int hp_profile_read(hp_solver* s, double* sweep_ms, int* launches, int64_t* bytes);
 
 /* Problem definition.  Replaces the scalar set-up at code.py:442-447 (omega, h, eta) and keeps a device
  * copy of the velocity model.  c_mat is the reference's (n+2) x (n+2) row-major float64 array (init_c*_mat,
