@@ -122,6 +122,8 @@ extern "C" int hp_precond_setup(hp_solver* s, int P, int K, int m_lo, int m_hi, 
     return hp_setup_strips(s, P, K, m_lo, m_hi, st);
 }
 
+// 0 = automatic, 1 = force the direct (no shared-memory staging) sweep kernel
+extern "C" int hp_set_sweep_variant(hp_solver* s, int v) { if (!s) return 1; s->sweep_variant = v; return 0; }
 extern "C" int64_t hp_precond_bytes(hp_solver* s) { return s ? s->bytes : 0; }
 extern "C" double hp_precond_setup_ms(hp_solver* s) { return s ? s->setup_ms : 0.0; }
 

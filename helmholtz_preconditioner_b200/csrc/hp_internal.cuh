@@ -63,7 +63,8 @@ struct hp_solver {
     cplx *f_low = nullptr, *f_invd = nullptr, *f_up = nullptr;   // [b][n]
     cplx* TF = nullptr;                                           // [b][n]   T_F u_F kept between the stages
     // sweep scratch
-    cplx *vbuf = nullptr, *gparts = nullptr, *xs = nullptr;
+    cplx *vbuf = nullptr, *gparts = nullptr, *gred = nullptr, *xs = nullptr;
+    int sweep_variant = 0;        // 0 = automatic (TMA double buffering when two packets fit in shared memory), 1 = direct
     unsigned int* bar = nullptr;
     int* status = nullptr;        // device flag: non-zero when a pivot vanished during setup
     // optional CUDA-event timing of the sweep launches (hp_profile_enable / hp_profile_read)

@@ -3,9 +3,10 @@
 // CTA streams its packet (csrc/hp_internal.cuh) once and the CTAs meet at two grid barriers:
 //
 //   S1  g   = Gp v_own                      (2b numbers per CTA)            -> gparts, v_own -> vbuf
+//       the last CTA of a leaf to arrive sums the K partial g in fixed order -> gred   (deterministic)
 //   ---- barrier A
 //   S2  y0  = Wp v_leaf                     (own rows of the leaf product)
-//       rho = e_b v_s - sum(gparts)         (separator right-hand sides)
+//       rho = e_b v_s - gred                (separator right-hand sides)
 //       x_S(own rows) = Np rho              (dense separator inverse)        -> xs
 //   ---- barrier B
 //   S3  y   = y0 - Gf^T x_left - Gl^T x_right, separator columns y_s = x_s[b-1]
@@ -13,7 +14,11 @@
 //                 backward  u_m <- u_m - y   (reference, :372-380 fused by linearity)  or  u_m <- y (paper)
 //       and the input of the next strip is formed in place (no barrier between S3 and the next S1).
 //
-// Only L2-resident exchange buffers cross CTAs (vbuf, gparts, xs, u); they are read with ld.global.cg.
+// Packets are independent of the data, so they are fetched ahead of the dependency chain: the TMA variant
+// double-buffers whole packets in shared memory with cp.async.bulk + mbarrier (issued one strip ahead, with an
+// L2 prefetch two strips ahead); the direct variant (packets too large for two shared-memory stages) reads
+// them from global memory behind an L2 prefetch.
+// Only L2-resident exchange buffers cross CTAs (vbuf, gparts, gred, xs, u); they are read with ld.global.cg.
 #include "hp_internal.cuh"
 
 #define HP_SWEEP_THREADS 256
@@ -28,8 +33,8 @@ struct HpSweepArgs {
     cplx* u;
     const cplx* vin;
     cplx* yout;
-    cplx *vbuf, *gparts, *xs;
-    unsigned int* bar;
+    cplx *vbuf, *gparts, *gred, *xs;
+    unsigned int* bar;        // [0] grid barrier counter, [4 + l] arrival tickets of leaf l
     const cplx *s2t, *is1t;
     double ih2;
 };
@@ -37,6 +42,33 @@ struct HpSweepArgs {
 __device__ __forceinline__ cplx ldcg(const cplx* p) {
     double2 v = __ldcg(reinterpret_cast<const double2*>(p));
     return v;
+}
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned int bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 __device__ __forceinline__ void hp_grid_barrier(unsigned int* bar, unsigned int& target, unsigned int nctas) {
@@ -67,8 +99,11 @@ __device__ __forceinline__ cplx hp_warp_sum2(cplx v) {
 // the x2 part for the pair (j, j+1), 1-based j
 __device__ __forceinline__ cplx hp_rowfac(const HpSweepArgs& a, int j) { return cscale(a.ih2, a.s2t[2 * j + 1]); }
 
-extern "C" __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs a) {
-    extern __shared__ double2 smem[];
+#define HP_BULK_CHUNK 32768u
+
+template <bool TMA>
+__global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = a.b, n = a.n, K = a.lay.K, P = a.lay.P, G = a.lay.G, QP = a.lay.QP, CW = a.lay.CW;
     const int NS = a.lay.NS, NSP = a.lay.NSP, NR = a.lay.NR;
     const int g = blockIdx.x, l = g / K, k = g % K;
@@ -76,28 +111,63 @@ extern "C" __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(H
     const int q = a.leaf_q[l], ls = a.leaf_start[l];
     const int lc0 = (q * k) / K, lc1 = (q * (k + 1)) / K, ncols = lc1 - lc0, c0 = ls + lc0;
     const int row0 = g * NR, nrows = max(0, min(NR, NS - row0));
+    const unsigned int pk_bytes = (unsigned int)(a.lay.PK * sizeof(cplx));
+    const size_t stage_bytes = ((size_t)pk_bytes + 127) & ~(size_t)127;
 
-    cplx* v_own = smem;                 // [CW]
+    cplx* stage0 = reinterpret_cast<cplx*>(smem_raw);
+    cplx* small = reinterpret_cast<cplx*>(smem_raw + (TMA ? 2 * stage_bytes : 0));
+    cplx* v_own = small;                // [CW]
     cplx* v_leaf = v_own + CW;          // [QP]
     cplx* y0 = v_leaf + QP;             // [CW]
     cplx* rho = y0 + CW;                // [NSP]
     cplx* xlr = rho + NSP;              // [2b]  x_left, x_right
     cplx* xrow = xlr + 2 * b;           // [NR+1] own rows of x_S
+    cplx* gp_s = xrow + NR + 1;         // [2b]  own partial g
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(gp_s + 2 * b);   // [2]
+    __shared__ int s_last;
 
     unsigned int target = 0;
     const int step = a.mode == 1 ? -1 : 1;
     const int nsteps = a.mode == 2 ? 1 : (a.mode == 0 ? a.m_to - a.m_from + 1 : a.m_from - a.m_to + 1);
     const cplx sgn = cmake(a.diag_mode == 0 ? 1.0 : -1.0, 0.0);
-
-    // input of the first strip
     int m = a.m_from;
+    const cplx* pk_base = a.packets + (size_t)g * a.lay.PK;
+    const size_t strip_stride = (size_t)G * a.lay.PK;
+
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // strip 0 -> stage 0, strip 1 -> stage 1, strip 2 -> L2
+            for (int sidx = 0; sidx < 2 && sidx < nsteps; ++sidx) {
+                const char* src = (const char*)(pk_base + (size_t)(m + sidx * step - a.m_lo) * strip_stride);
+                char* dst = (char*)smem_raw + sidx * stage_bytes;
+                mbar_expect_tx(&mbar[sidx], pk_bytes);
+                for (unsigned int o = 0; o < pk_bytes; o += HP_BULK_CHUNK)
+                    bulk_g2s(dst + o, src + o, min(HP_BULK_CHUNK, pk_bytes - o), &mbar[sidx]);
+            }
+            if (nsteps > 2) {
+                const char* src = (const char*)(pk_base + (size_t)(m + 2 * step - a.m_lo) * strip_stride);
+                for (unsigned int o = 0; o < pk_bytes; o += HP_BULK_CHUNK) bulk_prefetch_l2(src + o, min(HP_BULK_CHUNK, pk_bytes - o));
+            }
+        }
+    }
+
+    // input of the first strip; ubase = the u value the epilogue of this strip combines with y
+    cplx ubase = cmake(0.0, 0.0);
     if (tid < ncols) {
         int c = c0 + tid;
         cplx v;
         if (a.mode == 2) v = a.vin[c];
-        else if (a.mode == 0) v = ldcg(a.u + (size_t)(m - 1) * n + c);
+        else if (a.mode == 0) { v = ldcg(a.u + (size_t)(m - 1) * n + c); }
         else {
-            v = ldcg(a.u + (size_t)(m - 1) * n + c);
+            ubase = ldcg(a.u + (size_t)(m - 1) * n + c);
+            v = ubase;
             if (m < n) {
                 cplx cp = cmul(cmul(hp_rowfac(a, m), a.is1t[2 * (c + 1)]), sgn);
                 v = cfma(cp, ldcg(a.u + (size_t)m * n + c), v);
@@ -108,24 +178,67 @@ extern "C" __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(H
     __syncthreads();
 
     for (int it = 0; it < nsteps; ++it, m += step) {
-        const cplx* pk = a.packets + ((size_t)(m - a.m_lo) * G + g) * a.lay.PK;
+        const int mn = m + step;               // next strip
+        const bool more = it + 1 < nsteps;
+        const cplx* pk;
+        if (TMA) {
+            pk = reinterpret_cast<const cplx*>(smem_raw + (it & 1) * stage_bytes);
+        } else {
+            pk = pk_base + (size_t)(m - a.m_lo) * strip_stride;
+            if (more) {   // pull the next strip's packet towards L2 while this one is processed
+                const char* nx = (const char*)(pk_base + (size_t)(mn - a.m_lo) * strip_stride);
+                for (size_t o = (size_t)tid * 128; o < pk_bytes; o += (size_t)HP_SWEEP_THREADS * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+            }
+        }
         const cplx* Wp = pk;
         const cplx* Gp = pk + a.lay.offG;
         const cplx* Np = pk + a.lay.offN;
-        // pull the next strip's packet towards L2 while this one is processed
-        if (it + 1 < nsteps) {
-            const char* nx = (const char*)(a.packets + ((size_t)(m + step - a.m_lo) * G + g) * a.lay.PK);
-            size_t bytes = a.lay.PK * sizeof(cplx);
-            for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)HP_SWEEP_THREADS * 128)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+        // early loads of the u values the epilogue needs (not written by any other CTA)
+        cplx upre = cmake(0.0, 0.0), usep = cmake(0.0, 0.0);
+        if (tid < ncols) {
+            int c = c0 + tid;
+            if (a.mode == 0) upre = ldcg(a.u + (size_t)m * n + c);
+            else if (a.mode == 1 && more) upre = ldcg(a.u + (size_t)(mn - 1) * n + c);
         }
+        int sep_col = -1;
+        if (tid < nrows) {
+            int row = row0 + tid;
+            int j = row / b;
+            if (row - j * b == b - 1) {
+                sep_col = a.sep[j];
+                if (a.mode == 0) usep = ldcg(a.u + (size_t)m * n + sep_col);
+                else if (a.mode == 1) usep = ldcg(a.u + (size_t)(m - 1) * n + sep_col);
+            }
+        }
+        if (TMA) mbar_wait(&mbar[it & 1], (it >> 1) & 1);
         // ---- S1
         if (tid < ncols) a.vbuf[c0 + tid] = v_own[tid];
         for (int kap = warp; kap < 2 * b; kap += nwarps) {
             cplx acc = cmake(0.0, 0.0);
             for (int cc = lane; cc < ncols; cc += 32) acc = cfma(Gp[(size_t)kap * CW + cc], v_own[cc], acc);
             acc = hp_warp_sum2(acc);
-            if (lane == 0) a.gparts[(size_t)g * 2 * b + kap] = acc;
+            if (lane == 0) gp_s[kap] = acc;
+        }
+        __syncthreads();
+        if (K == 1) {
+            if (tid < 2 * b) a.gred[(size_t)l * 2 * b + tid] = gp_s[tid];
+        } else {
+            if (tid < 2 * b) a.gparts[(size_t)g * 2 * b + tid] = gp_s[tid];
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                unsigned int old = atomicAdd(a.bar + 4 + l, 1u);
+                s_last = ((old % (unsigned int)K) == (unsigned int)(K - 1));
+                if (s_last) __threadfence();
+            }
+            __syncthreads();
+            if (s_last && tid < 2 * b) {
+                cplx acc = cmake(0.0, 0.0);
+                for (int kk = 0; kk < K; ++kk)
+                    acc = cadd(acc, kk == k ? gp_s[tid] : ldcg(a.gparts + (size_t)(l * K + kk) * 2 * b + tid));
+                a.gred[(size_t)l * 2 * b + tid] = acc;
+            }
         }
         hp_grid_barrier(a.bar, target, G);
         // ---- S2
@@ -133,11 +246,8 @@ extern "C" __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(H
         if (nrows > 0) {
             for (int e = tid; e < NS; e += HP_SWEEP_THREADS) {
                 int j = e / b, kap = e - j * b;
-                cplx acc = cmake(0.0, 0.0);
-                for (int kk = 0; kk < K; ++kk) {
-                    acc = csub(acc, ldcg(a.gparts + ((size_t)(j * K + kk) * 2 + 1) * b + kap));        // Gl of leaf j
-                    acc = csub(acc, ldcg(a.gparts + ((size_t)((j + 1) * K + kk) * 2) * b + kap));      // Gf of leaf j+1
-                }
+                cplx acc = cneg(cadd(ldcg(a.gred + ((size_t)j * 2 + 1) * b + kap),           // Gl of leaf j
+                                     ldcg(a.gred + ((size_t)(j + 1) * 2) * b + kap)));       // Gf of leaf j+1
                 if (kap == b - 1) {
                     int s = a.sep[j];
                     cplx vs;
@@ -155,19 +265,21 @@ extern "C" __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(H
             }
         }
         __syncthreads();
-        for (int cc = warp; cc < ncols; cc += nwarps) {
-            cplx acc = cmake(0.0, 0.0);
-            const cplx* wr = Wp + (size_t)cc * QP;
-            for (int c = lane; c < q; c += 32) acc = cfma(wr[c], v_leaf[c], acc);
-            acc = hp_warp_sum2(acc);
-            if (lane == 0) y0[cc] = acc;
-        }
-        for (int rr = warp; rr < nrows; rr += nwarps) {
+        for (int rr = warp; rr < nrows; rr += nwarps) {      // separator rows first: they are on the critical path
             cplx acc = cmake(0.0, 0.0);
             const cplx* nr = Np + (size_t)rr * NSP;
+#pragma unroll 4
             for (int e = lane; e < NS; e += 32) acc = cfma(nr[e], rho[e], acc);
             acc = hp_warp_sum2(acc);
             if (lane == 0) { a.xs[row0 + rr] = acc; xrow[rr] = acc; }
+        }
+        for (int cc = warp; cc < ncols; cc += nwarps) {
+            cplx acc = cmake(0.0, 0.0);
+            const cplx* wr = Wp + (size_t)cc * QP;
+#pragma unroll 4
+            for (int c = lane; c < q; c += 32) acc = cfma(wr[c], v_leaf[c], acc);
+            acc = hp_warp_sum2(acc);
+            if (lane == 0) y0[cc] = acc;
         }
         hp_grid_barrier(a.bar, target, G);
         // ---- S3
@@ -177,47 +289,56 @@ extern "C" __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(H
             xlr[tid] = (j >= 0 && j < P - 1) ? ldcg(a.xs + (size_t)j * b + kap) : cmake(0.0, 0.0);
         }
         __syncthreads();
-        const int mn = m + step;               // next strip
-        const bool more = it + 1 < nsteps;
         if (tid < ncols) {
             int c = c0 + tid;
             cplx y = y0[tid];
+#pragma unroll 4
             for (int kap = 0; kap < 2 * b; ++kap) y = cfms(Gp[(size_t)kap * CW + tid], xlr[kap], y);
             if (a.mode == 2) {
                 a.yout[c] = y;
             } else if (a.mode == 0) {
                 // u_{m+1} -= c3(row m+1) y ; the result is the input of strip m+1
                 cplx cp = cmul(hp_rowfac(a, m), a.is1t[2 * (c + 1)]);
-                cplx un = cfms(cp, y, ldcg(a.u + (size_t)m * n + c));
+                cplx un = cfms(cp, y, upre);
                 a.u[(size_t)m * n + c] = un;
                 v_own[tid] = un;
             } else {
-                cplx un = a.diag_mode == 0 ? csub(ldcg(a.u + (size_t)(m - 1) * n + c), y) : y;
+                cplx un = a.diag_mode == 0 ? csub(ubase, y) : y;
                 a.u[(size_t)(m - 1) * n + c] = un;
                 if (more) {
                     // input of strip m-1: u_{m-1} (+/-) c4(row m-1) u_m
                     cplx cp = cmul(cmul(hp_rowfac(a, mn), a.is1t[2 * (c + 1)]), sgn);
-                    v_own[tid] = cfma(cp, un, ldcg(a.u + (size_t)(mn - 1) * n + c));
+                    ubase = upre;
+                    v_own[tid] = cfma(cp, un, upre);
                 }
             }
         }
         // separator columns: the CTA that computed row (j, b-1) of x_S owns the update of column sep[j]
-        if (tid < nrows) {
-            int row = row0 + tid;
-            int j = row / b, kap = row - j * b;
-            if (kap == b - 1) {
-                int s = a.sep[j];
-                cplx y = xrow[tid];
-                if (a.mode == 2) a.yout[s] = y;
-                else if (a.mode == 0) {
-                    cplx cp = cmul(hp_rowfac(a, m), a.is1t[2 * (s + 1)]);
-                    a.u[(size_t)m * n + s] = cfms(cp, y, ldcg(a.u + (size_t)m * n + s));
-                } else {
-                    a.u[(size_t)(m - 1) * n + s] = a.diag_mode == 0 ? csub(ldcg(a.u + (size_t)(m - 1) * n + s), y) : y;
-                }
+        if (sep_col >= 0) {
+            cplx y = xrow[tid];
+            if (a.mode == 2) a.yout[sep_col] = y;
+            else if (a.mode == 0) {
+                cplx cp = cmul(hp_rowfac(a, m), a.is1t[2 * (sep_col + 1)]);
+                a.u[(size_t)m * n + sep_col] = cfms(cp, y, usep);
+            } else {
+                a.u[(size_t)(m - 1) * n + sep_col] = a.diag_mode == 0 ? csub(usep, y) : y;
             }
         }
         __syncthreads();
+        if (TMA && tid == 0) {
+            // every thread is done with this stage: refill it with the packet two strips ahead
+            if (it + 2 < nsteps) {
+                const char* src = (const char*)(pk_base + (size_t)(m + 2 * step - a.m_lo) * strip_stride);
+                char* dst = (char*)smem_raw + (it & 1) * stage_bytes;
+                mbar_expect_tx(&mbar[it & 1], pk_bytes);
+                for (unsigned int o = 0; o < pk_bytes; o += HP_BULK_CHUNK)
+                    bulk_g2s(dst + o, src + o, min(HP_BULK_CHUNK, pk_bytes - o), &mbar[it & 1]);
+            }
+            if (it + 3 < nsteps) {
+                const char* src = (const char*)(pk_base + (size_t)(m + 3 * step - a.m_lo) * strip_stride);
+                for (unsigned int o = 0; o < pk_bytes; o += HP_BULK_CHUNK) bulk_prefetch_l2(src + o, min(HP_BULK_CHUNK, pk_bytes - o));
+            }
+        }
     }
 }
 
@@ -237,21 +358,24 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     a.packets = s->packets; a.m_lo = s->m_lo;
     a.mode = mode; a.m_from = m_from; a.m_to = m_to; a.diag_mode = diag_mode;
     a.u = u; a.vin = vin; a.yout = yout;
-    a.vbuf = s->vbuf; a.gparts = s->gparts; a.xs = s->xs; a.bar = s->bar;
+    a.vbuf = s->vbuf; a.gparts = s->gparts; a.gred = s->gred; a.xs = s->xs; a.bar = s->bar;
     a.s2t = s->s2t; a.is1t = s->is1t;
     a.ih2 = 1.0 / (s->pml.h * s->pml.h);
     const HpLayout& L = s->lay;
-    size_t smem = sizeof(cplx) * ((size_t)2 * L.CW + L.QP + L.NSP + 2 * s->b + L.NR + 1);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        HP_CUDA(cudaFuncSetAttribute(hp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
-    HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int), st));
+    size_t small = sizeof(cplx) * ((size_t)2 * L.CW + L.QP + L.NSP + 4 * s->b + L.NR + 1) + 2 * sizeof(unsigned long long);
+    size_t stage = (L.PK * sizeof(cplx) + 127) & ~(size_t)127;
+    int max_smem = 0, dev = 0;
+    HP_CUDA(cudaGetDevice(&dev));
+    HP_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    bool tma = s->sweep_variant != 1 && 2 * stage + small + 1024 <= (size_t)max_smem;
+    size_t smem = small + (tma ? 2 * stage : 0);
+    const void* fn = tma ? (const void*)hp_sweep_kernel<true> : (const void*)hp_sweep_kernel<false>;
+    if (smem > 48 * 1024) HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int) * (4 + L.P), st));
     void* args[] = {&a};
     hp_count_launch();
     hp_profile_begin(s, st);
-    HP_CUDA(cudaLaunchCooperativeKernel((const void*)hp_sweep_kernel, dim3(L.G), dim3(HP_SWEEP_THREADS), args, smem, st));
+    HP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.G), dim3(HP_SWEEP_THREADS), args, smem, st));
     hp_profile_end(s, st, (int64_t)(hi - lo + 1) * ((int64_t)L.G * L.PK + 3 * (int64_t)s->n) * (int64_t)sizeof(cplx));
     return 0;
 }

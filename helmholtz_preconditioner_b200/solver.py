@@ -112,6 +112,11 @@ class HelmholtzSolver:
         self.m_lo, self.m_hi = m_lo, m_hi
         return self
 
+    def set_sweep_variant(self, variant):
+        """0 = automatic (TMA-staged packets when they fit), 1 = direct global loads."""
+        _lib.check(self.lib.hp_set_sweep_variant(self.handle, int(variant)), "hp_set_sweep_variant")
+        return self
+
     @property
     def precond_bytes(self):
         return int(self.lib.hp_precond_bytes(self.handle))

@@ -68,6 +68,8 @@ int hp_precond_setup(hp_solver* s, int P, int K, int m_lo, int m_hi, void* strea
 /* bytes of device memory held by the strip factorisation, and the device time the last setup took */
 int64_t hp_precond_bytes(hp_solver* s);
 double hp_precond_setup_ms(hp_solver* s);
+/* sweep kernel variant: 0 = automatic (TMA-staged packets when two fit in shared memory), 1 = direct loads */
+int hp_set_sweep_variant(hp_solver* s, int variant);
 
 /* The three stages of algo2_4 (code.py:356-385), operating in place on the field u_dev (n*n complex):
  *   hp_front_begin   : T_F u_F = H_F^{-1} u_F kept aside, u_{b+1} -= A_{b+1,F} T_F u_F        (:364-365)
