@@ -122,6 +122,15 @@ extern "C" int hp_precond_setup(hp_solver* s, int P, int K, int m_lo, int m_hi, 
     return hp_setup_strips(s, P, K, m_lo, m_hi, st);
 }
 
+// developer hook: per-phase cycle counters of the sweep kernel.  on=1 allocates/zeroes, read copies [G][8] to host
+extern "C" int hp_debug_phases(hp_solver* s, int on, long long* out_host) {
+    if (!s || !s->packets) return 1;
+    size_t sz = sizeof(long long) * 8 * s->lay.G;
+    if (on && !s->dbg) { HP_CUDA(cudaMalloc(&s->dbg, sz)); HP_CUDA(cudaMemset(s->dbg, 0, sz)); }
+    if (out_host && s->dbg) HP_CUDA(cudaMemcpy(out_host, s->dbg, sz, cudaMemcpyDeviceToHost));
+    if (!on && s->dbg) { cudaFree(s->dbg); s->dbg = nullptr; }
+    return 0;
+}
 // 0 = automatic, 1 = force the direct (no shared-memory staging) sweep kernel
 extern "C" int hp_set_sweep_variant(hp_solver* s, int v) { if (!s) return 1; s->sweep_variant = v; return 0; }
 extern "C" int64_t hp_precond_bytes(hp_solver* s) { return s ? s->bytes : 0; }

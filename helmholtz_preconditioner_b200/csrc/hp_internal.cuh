@@ -64,6 +64,7 @@ struct hp_solver {
     cplx* TF = nullptr;                                           // [b][n]   T_F u_F kept between the stages
     // sweep scratch
     cplx *vbuf = nullptr, *gparts = nullptr, *gred = nullptr, *xs = nullptr;
+    long long* dbg = nullptr;     // optional per-phase cycle counters of the sweep kernel [G][8]
     int sweep_variant = 0;        // 0 = automatic (TMA double buffering when two packets fit in shared memory), 1 = direct
     unsigned int* bar = nullptr;
     int* status = nullptr;        // device flag: non-zero when a pivot vanished during setup

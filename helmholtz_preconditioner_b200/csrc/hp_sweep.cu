@@ -37,6 +37,7 @@ struct HpSweepArgs {
     unsigned int* bar;        // [0] grid barrier counter, [4 + l] arrival tickets of leaf l
     const cplx *s2t, *is1t;
     double ih2;
+    long long* dbg;           // optional [G][8] per-phase cycle sums (thread 0 of every CTA), NULL = off
 };
 
 __device__ __forceinline__ cplx ldcg(const cplx* p) {
@@ -75,13 +76,11 @@ __device__ __forceinline__ void hp_grid_barrier(unsigned int* bar, unsigned int&
     __syncthreads();
     if (threadIdx.x == 0) {
         target += nctas;
-        __threadfence();
-        atomicAdd(bar, 1u);
+        asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned int v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
         } while ((int)(v - target) < 0);
-        __threadfence();
     }
     __syncthreads();
 }
@@ -126,6 +125,8 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(gp_s + 2 * b);   // [2]
     __shared__ int s_last;
 
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
+#define HP_TICK(i) do { if (a.dbg && tid == 0) { long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
     unsigned int target = 0;
     const int step = a.mode == 1 ? -1 : 1;
     const int nsteps = a.mode == 2 ? 1 : (a.mode == 0 ? a.m_to - a.m_from + 1 : a.m_from - a.m_to + 1);
@@ -211,7 +212,9 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
                 else if (a.mode == 1) usep = ldcg(a.u + (size_t)(m - 1) * n + sep_col);
             }
         }
+        if (a.dbg && tid == 0) tprev = clock64();
         if (TMA) mbar_wait(&mbar[it & 1], (it >> 1) & 1);
+        HP_TICK(0);
         // ---- S1
         if (tid < ncols) a.vbuf[c0 + tid] = v_own[tid];
         for (int kap = warp; kap < 2 * b; kap += nwarps) {
@@ -227,10 +230,9 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
             if (tid < 2 * b) a.gparts[(size_t)g * 2 * b + tid] = gp_s[tid];
             __syncthreads();
             if (tid == 0) {
-                __threadfence();
-                unsigned int old = atomicAdd(a.bar + 4 + l, 1u);
+                unsigned int old;
+                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.bar + 4 + l) : "memory");
                 s_last = ((old % (unsigned int)K) == (unsigned int)(K - 1));
-                if (s_last) __threadfence();
             }
             __syncthreads();
             if (s_last && tid < 2 * b) {
@@ -240,7 +242,10 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
                 a.gred[(size_t)l * 2 * b + tid] = acc;
             }
         }
+        __syncthreads();
+        HP_TICK(1);
         hp_grid_barrier(a.bar, target, G);
+        HP_TICK(2);
         // ---- S2
         for (int c = tid; c < q; c += HP_SWEEP_THREADS) v_leaf[c] = ldcg(a.vbuf + ls + c);
         if (nrows > 0) {
@@ -281,7 +286,10 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
             acc = hp_warp_sum2(acc);
             if (lane == 0) y0[cc] = acc;
         }
+        __syncthreads();
+        HP_TICK(3);
         hp_grid_barrier(a.bar, target, G);
+        HP_TICK(4);
         // ---- S3
         if (tid < 2 * b) {
             int side = tid / b, kap = tid - side * b;
@@ -325,6 +333,7 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
             }
         }
         __syncthreads();
+        HP_TICK(5);
         if (TMA && tid == 0) {
             // every thread is done with this stage: refill it with the packet two strips ahead
             if (it + 2 < nsteps) {
@@ -340,6 +349,8 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
             }
         }
     }
+    if (a.dbg && tid == 0)
+        for (int i = 0; i < 8; ++i) a.dbg[(size_t)g * 8 + i] = tacc[i];
 }
 
 int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout, int m_from, int m_to,
@@ -361,6 +372,7 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     a.vbuf = s->vbuf; a.gparts = s->gparts; a.gred = s->gred; a.xs = s->xs; a.bar = s->bar;
     a.s2t = s->s2t; a.is1t = s->is1t;
     a.ih2 = 1.0 / (s->pml.h * s->pml.h);
+    a.dbg = s->dbg;
     const HpLayout& L = s->lay;
     size_t small = sizeof(cplx) * ((size_t)2 * L.CW + L.QP + L.NSP + 4 * s->b + L.NR + 1) + 2 * sizeof(unsigned long long);
     size_t stage = (L.PK * sizeof(cplx) + 127) & ~(size_t)127;
