@@ -29,6 +29,7 @@ SIGNATURES = {
     "hp_csr_matvec": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_precond_setup": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "hp_debug_phases": (_i, [_vp, _i, _vp]),
+    "hp_sweep_status": (_i, [_vp]),
     "hp_set_sweep_variant": (_i, [_vp, _i]),
     "hp_precond_bytes": (_i64, [_vp]),
     "hp_precond_setup_ms": (_d, [_vp]),

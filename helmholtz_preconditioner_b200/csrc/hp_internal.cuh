@@ -63,7 +63,7 @@ struct hp_solver {
     cplx *f_low = nullptr, *f_invd = nullptr, *f_up = nullptr;   // [b][n]
     cplx* TF = nullptr;                                           // [b][n]   T_F u_F kept between the stages
     // sweep scratch
-    cplx *vbuf = nullptr, *gparts = nullptr, *gred = nullptr, *xs = nullptr;
+    cplx* xch = nullptr;          // exchange ring of the sweep kernel (csrc/hp_sweep.cu)
     long long* dbg = nullptr;     // optional per-phase cycle counters of the sweep kernel [G][8]
     int sweep_variant = 0;        // 0 = automatic (TMA double buffering when two packets fit in shared memory), 1 = direct
     unsigned int* bar = nullptr;

@@ -174,10 +174,7 @@ void hp_free_strips(hp_solver* s) {
     cudaFree(s->leaf_start); s->leaf_start = nullptr;
     cudaFree(s->leaf_q); s->leaf_q = nullptr;
     cudaFree(s->sep); s->sep = nullptr;
-    cudaFree(s->vbuf); s->vbuf = nullptr;
-    cudaFree(s->gparts); s->gparts = nullptr;
-    cudaFree(s->gred); s->gred = nullptr;
-    cudaFree(s->xs); s->xs = nullptr;
+    cudaFree(s->xch); s->xch = nullptr;
     cudaFree(s->bar); s->bar = nullptr;
     s->m_lo = 0; s->m_hi = -1; s->bytes = 0;
 }
@@ -211,10 +208,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     size_t pbytes = (size_t)nstrips * L.G * L.PK * sizeof(cplx);
     HP_CUDA(cudaMalloc(&s->packets, pbytes));
     HP_CUDA(cudaMemsetAsync(s->packets, 0, pbytes, st));
-    HP_CUDA(cudaMalloc(&s->vbuf, sizeof(cplx) * n));
-    HP_CUDA(cudaMalloc(&s->gparts, sizeof(cplx) * L.G * 2 * b));
-    HP_CUDA(cudaMalloc(&s->gred, sizeof(cplx) * L.P * 2 * b));
-    HP_CUDA(cudaMalloc(&s->xs, sizeof(cplx) * L.NSP));
+    HP_CUDA(cudaMalloc(&s->xch, sizeof(cplx) * 4 * ((size_t)n + (size_t)L.G * 2 * b + (size_t)L.P * 2 * b + L.NSP + L.P)));
     HP_CUDA(cudaMalloc(&s->bar, sizeof(unsigned int) * (4 + L.P)));
     HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int) * (4 + L.P), st));
     HP_CUDA(cudaMemsetAsync(s->status, 0, sizeof(int), st));

@@ -1,27 +1,33 @@
 // The sweeps of algo2_4 (/root/reference/code.py:366-380): a chain of strip solves y = T_m v, each of which
 // depends on the previous one.  One persistent cooperative kernel walks the whole chain; per strip every
-// CTA streams its packet (csrc/hp_internal.cuh) once and the CTAs meet at two grid barriers:
+// CTA streams its packet (csrc/hp_internal.cuh) once.
 //
-//   S1  g   = Gp v_own                      (2b numbers per CTA)            -> gparts, v_own -> vbuf
-//       the last CTA of a leaf to arrive sums the K partial g in fixed order -> gred   (deterministic)
-//   ---- barrier A
-//   S2  y0  = Wp v_leaf                     (own rows of the leaf product)
-//       rho = e_b v_s - gred                (separator right-hand sides)
-//       x_S(own rows) = Np rho              (dense separator inverse)        -> xs
-//   ---- barrier B
-//   S3  y   = y0 - Gf^T x_left - Gl^T x_right, separator columns y_s = x_s[b-1]
+//   S1  g   = Gp v_own                      (2b numbers per CTA)         -> exchange: V (own columns), GP
+//       the first CTA of a leaf sums the K partial g in fixed order       -> exchange: GR   (deterministic)
+//   S2  y0  = Wp v_leaf                     (own rows of the leaf product; v_leaf <- exchange V)
+//       rho = e_b v_s - GR                  (separator right-hand sides;   <- exchange GR, VS)
+//       x_S(own rows) = Np rho              (dense separator inverse)     -> exchange: XS
+//   S3  y   = y0 - Gf^T x_left - Gl^T x_right  (<- exchange XS), separator columns y_s = x_s[b-1]
 //       epilogue: forward   u_{m+1} -= A_{m+1,m} y                           (code.py:370)
 //                 backward  u_m <- u_m - y   (reference, :372-380 fused by linearity)  or  u_m <- y (paper)
-//       and the input of the next strip is formed in place (no barrier between S3 and the next S1).
+//       and the input of the next strip is formed in place (S3 runs straight into the next S1).
+//
+// There is no grid barrier.  CTAs exchange the few numbers that cross them through a ring of four L2-resident
+// slots (slot = strip counter mod 4) in which every 8-byte word validates itself: the ring is filled with
+// 0xFF bytes (a NaN no arithmetic produces), producers overwrite it with data, consumers spin on the data word
+// itself until it differs from the sentinel - one L2 round trip per hand-over, no fences, no atomics.  A
+// producer re-arms its words two strips after writing them; by then every consumer has moved on, because a
+// CTA cannot finish strip t+1 before all CTAs have finished strip t (S2 needs GR from every leaf).
 //
 // Packets are independent of the data, so they are fetched ahead of the dependency chain: the TMA variant
 // double-buffers whole packets in shared memory with cp.async.bulk + mbarrier (issued one strip ahead, with an
 // L2 prefetch two strips ahead); the direct variant (packets too large for two shared-memory stages) reads
 // them from global memory behind an L2 prefetch.
-// Only L2-resident exchange buffers cross CTAs (vbuf, gparts, gred, xs, u); they are read with ld.global.cg.
 #include "hp_internal.cuh"
 
 #define HP_SWEEP_THREADS 256
+#define HP_RING 4
+#define HP_SPIN_LIMIT (1u << 24)
 
 struct HpSweepArgs {
     int n, b;
@@ -33,8 +39,9 @@ struct HpSweepArgs {
     cplx* u;
     const cplx* vin;
     cplx* yout;
-    cplx *vbuf, *gparts, *gred, *xs;
-    unsigned int* bar;        // [0] grid barrier counter, [4 + l] arrival tickets of leaf l
+    cplx* xch;                // exchange ring: HP_RING slots of slot_stride complex numbers
+    size_t oGP, oGR, oXS, oVS, slot_stride;
+    unsigned int* bar;        // [1] abort flag (a spin ran into HP_SPIN_LIMIT)
     const cplx *s2t, *is1t;
     double ih2;
     long long* dbg;           // optional [G][8] per-phase cycle sums (thread 0 of every CTA), NULL = off
@@ -42,6 +49,32 @@ struct HpSweepArgs {
 
 __device__ __forceinline__ cplx ldcg(const cplx* p) {
     double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+    return v;
+}
+
+// ---- self-validating exchange words -----------------------------------------------------------------
+#define HP_SENTINEL 0xFFFFFFFFFFFFFFFFull
+__device__ __forceinline__ void xput(cplx* p, cplx v) {
+    asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void xarm(cplx* p) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(p), "l"(HP_SENTINEL) : "memory");
+}
+__device__ __forceinline__ bool xtry(const cplx* p, cplx& v) {
+    unsigned long long lo, hi;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+    v.x = __longlong_as_double((long long)lo);
+    v.y = __longlong_as_double((long long)hi);
+    return lo != HP_SENTINEL && hi != HP_SENTINEL;
+}
+// spin until the word is valid; on a runaway spin raise the abort flag (the kernel then terminates)
+__device__ __forceinline__ cplx xget(const cplx* p, unsigned int* abort_flag) {
+    cplx v;
+    unsigned int spins = 0;
+    while (!xtry(p, v)) {
+        if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); break; }
+        if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) break;
+    }
     return v;
 }
 
@@ -72,22 +105,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int 
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ void hp_grid_barrier(unsigned int* bar, unsigned int& target, unsigned int nctas) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += nctas;
-        asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-        unsigned int v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        } while ((int)(v - target) < 0);
-    }
-    __syncthreads();
-}
-
 __device__ __forceinline__ cplx hp_warp_sum2(cplx v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    return v;
+}
+// sum over the aligned group of 8 lanes a thread belongs to
+__device__ __forceinline__ cplx hp_oct_sum2(cplx v) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
         v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
         v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
     }
@@ -107,13 +136,14 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
     const int NS = a.lay.NS, NSP = a.lay.NSP, NR = a.lay.NR;
     const int g = blockIdx.x, l = g / K, k = g % K;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = HP_SWEEP_THREADS / 32;
+    const int oct = tid >> 3, lane8 = tid & 7, nocts = HP_SWEEP_THREADS / 8;
     const int q = a.leaf_q[l], ls = a.leaf_start[l];
     const int lc0 = (q * k) / K, lc1 = (q * (k + 1)) / K, ncols = lc1 - lc0, c0 = ls + lc0;
     const int row0 = g * NR, nrows = max(0, min(NR, NS - row0));
     const unsigned int pk_bytes = (unsigned int)(a.lay.PK * sizeof(cplx));
     const size_t stage_bytes = ((size_t)pk_bytes + 127) & ~(size_t)127;
+    unsigned int* abort_flag = a.bar + 1;
 
-    cplx* stage0 = reinterpret_cast<cplx*>(smem_raw);
     cplx* small = reinterpret_cast<cplx*>(smem_raw + (TMA ? 2 * stage_bytes : 0));
     cplx* v_own = small;                // [CW]
     cplx* v_leaf = v_own + CW;          // [QP]
@@ -122,12 +152,12 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
     cplx* xlr = rho + NSP;              // [2b]  x_left, x_right
     cplx* xrow = xlr + 2 * b;           // [NR+1] own rows of x_S
     cplx* gp_s = xrow + NR + 1;         // [2b]  own partial g
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(gp_s + 2 * b);   // [2]
-    __shared__ int s_last;
+    cplx* ypart = gp_s + 2 * b;         // [8][CW] partial sums of the S3 correction
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ypart + (size_t)nwarps * CW);   // [2]
 
+    __shared__ unsigned int s_abort;
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
 #define HP_TICK(i) do { if (a.dbg && tid == 0) { long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
-    unsigned int target = 0;
     const int step = a.mode == 1 ? -1 : 1;
     const int nsteps = a.mode == 2 ? 1 : (a.mode == 0 ? a.m_to - a.m_from + 1 : a.m_from - a.m_to + 1);
     const cplx sgn = cmake(a.diag_mode == 0 ? 1.0 : -1.0, 0.0);
@@ -159,8 +189,15 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
         }
     }
 
+    // the separator column this thread owns (the CTA that computes row (j, b-1) of x_S updates column sep[j])
+    int sep_j = -1, sep_col = -1;
+    if (tid < nrows) {
+        int row = row0 + tid;
+        int j = row / b;
+        if (row - j * b == b - 1) { sep_j = j; sep_col = a.sep[j]; }
+    }
     // input of the first strip; ubase = the u value the epilogue of this strip combines with y
-    cplx ubase = cmake(0.0, 0.0);
+    cplx ubase = cmake(0.0, 0.0), usbase = cmake(0.0, 0.0);
     if (tid < ncols) {
         int c = c0 + tid;
         cplx v;
@@ -176,11 +213,28 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
         }
         v_own[tid] = v;
     }
+    if (sep_col >= 0) {
+        cplx v;
+        if (a.mode == 2) v = a.vin[sep_col];
+        else if (a.mode == 0) v = ldcg(a.u + (size_t)(m - 1) * n + sep_col);
+        else {
+            usbase = ldcg(a.u + (size_t)(m - 1) * n + sep_col);
+            v = usbase;
+            if (m < n) {
+                cplx cp = cmul(cmul(hp_rowfac(a, m), a.is1t[2 * (sep_col + 1)]), sgn);
+                v = cfma(cp, ldcg(a.u + (size_t)m * n + sep_col), v);
+            }
+        }
+        xput(a.xch + a.oVS + sep_j, v);                 // slot 0
+    }
     __syncthreads();
 
     for (int it = 0; it < nsteps; ++it, m += step) {
         const int mn = m + step;               // next strip
         const bool more = it + 1 < nsteps;
+        cplx* slot = a.xch + (size_t)(it & (HP_RING - 1)) * a.slot_stride;
+        cplx* slot_next = a.xch + (size_t)((it + 1) & (HP_RING - 1)) * a.slot_stride;
+        cplx* slot_arm = a.xch + (size_t)((it + 2) & (HP_RING - 1)) * a.slot_stride;
         const cplx* pk;
         if (TMA) {
             pk = reinterpret_cast<const cplx*>(smem_raw + (it & 1) * stage_bytes);
@@ -195,113 +249,115 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
         const cplx* Wp = pk;
         const cplx* Gp = pk + a.lay.offG;
         const cplx* Np = pk + a.lay.offN;
-        // early loads of the u values the epilogue needs (not written by any other CTA)
+        // early loads of the u values the epilogue needs (written by no other CTA)
         cplx upre = cmake(0.0, 0.0), usep = cmake(0.0, 0.0);
         if (tid < ncols) {
             int c = c0 + tid;
             if (a.mode == 0) upre = ldcg(a.u + (size_t)m * n + c);
             else if (a.mode == 1 && more) upre = ldcg(a.u + (size_t)(mn - 1) * n + c);
         }
-        int sep_col = -1;
-        if (tid < nrows) {
-            int row = row0 + tid;
-            int j = row / b;
-            if (row - j * b == b - 1) {
-                sep_col = a.sep[j];
-                if (a.mode == 0) usep = ldcg(a.u + (size_t)m * n + sep_col);
-                else if (a.mode == 1) usep = ldcg(a.u + (size_t)(m - 1) * n + sep_col);
-            }
+        if (sep_col >= 0) {
+            if (a.mode == 0) usep = ldcg(a.u + (size_t)m * n + sep_col);
+            else if (a.mode == 1 && more) usep = ldcg(a.u + (size_t)(mn - 1) * n + sep_col);
         }
         if (a.dbg && tid == 0) tprev = clock64();
         if (TMA) mbar_wait(&mbar[it & 1], (it >> 1) & 1);
         HP_TICK(0);
-        // ---- S1
-        if (tid < ncols) a.vbuf[c0 + tid] = v_own[tid];
-        for (int kap = warp; kap < 2 * b; kap += nwarps) {
+        // ---- S1: publish own columns, partial interface data
+        if (K > 1 && tid < ncols) xput(slot + c0 + tid, v_own[tid]);
+        for (int kap = oct; kap < 2 * b; kap += nocts) {
             cplx acc = cmake(0.0, 0.0);
-            for (int cc = lane; cc < ncols; cc += 32) acc = cfma(Gp[(size_t)kap * CW + cc], v_own[cc], acc);
-            acc = hp_warp_sum2(acc);
-            if (lane == 0) gp_s[kap] = acc;
-        }
-        __syncthreads();
-        if (K == 1) {
-            if (tid < 2 * b) a.gred[(size_t)l * 2 * b + tid] = gp_s[tid];
-        } else {
-            if (tid < 2 * b) a.gparts[(size_t)g * 2 * b + tid] = gp_s[tid];
-            __syncthreads();
-            if (tid == 0) {
-                unsigned int old;
-                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.bar + 4 + l) : "memory");
-                s_last = ((old % (unsigned int)K) == (unsigned int)(K - 1));
-            }
-            __syncthreads();
-            if (s_last && tid < 2 * b) {
-                cplx acc = cmake(0.0, 0.0);
-                for (int kk = 0; kk < K; ++kk)
-                    acc = cadd(acc, kk == k ? gp_s[tid] : ldcg(a.gparts + (size_t)(l * K + kk) * 2 * b + tid));
-                a.gred[(size_t)l * 2 * b + tid] = acc;
+            const cplx* gr = Gp + (size_t)kap * CW;
+            for (int cc = lane8; cc < ncols; cc += 8) acc = cfma(gr[cc], v_own[cc], acc);
+            acc = hp_oct_sum2(acc);
+            if (lane8 == 0) {
+                if (K == 1) xput(slot + a.oGR + (size_t)l * 2 * b + kap, acc);
+                else if (k == 0) gp_s[kap] = acc;
+                else xput(slot + a.oGP + (size_t)g * 2 * b + kap, acc);
             }
         }
-        __syncthreads();
+        // re-arm what this CTA wrote two strips ago (slot it+2 = it-2 mod 4)
+        if (K > 1 && tid < ncols) xarm(slot_arm + c0 + tid);
+        if (tid < 2 * b) {
+            if (K > 1 && k > 0) xarm(slot_arm + a.oGP + (size_t)g * 2 * b + tid);
+            if (k == 0) xarm(slot_arm + a.oGR + (size_t)l * 2 * b + tid);
+        }
+        if (tid < nrows) xarm(slot_arm + a.oXS + row0 + tid);
+        if (sep_col >= 0) xarm(slot_arm + a.oVS + sep_j);
         HP_TICK(1);
-        hp_grid_barrier(a.bar, target, G);
+        if (K > 1 && k == 0) {
+            __syncthreads();
+            if (tid < 2 * b) {
+                cplx acc = gp_s[tid];
+                for (int kk = 1; kk < K; ++kk) acc = cadd(acc, xget(slot + a.oGP + (size_t)(g + kk) * 2 * b + tid, abort_flag));
+                xput(slot + a.oGR + (size_t)l * 2 * b + tid, acc);
+            }
+        }
         HP_TICK(2);
         // ---- S2
-        for (int c = tid; c < q; c += HP_SWEEP_THREADS) v_leaf[c] = ldcg(a.vbuf + ls + c);
+        for (int c = tid; c < q; c += HP_SWEEP_THREADS)
+            v_leaf[c] = (c >= lc0 && c < lc1) ? v_own[c - lc0] : xget(slot + ls + c, abort_flag);
         if (nrows > 0) {
             for (int e = tid; e < NS; e += HP_SWEEP_THREADS) {
                 int j = e / b, kap = e - j * b;
-                cplx acc = cneg(cadd(ldcg(a.gred + ((size_t)j * 2 + 1) * b + kap),           // Gl of leaf j
-                                     ldcg(a.gred + ((size_t)(j + 1) * 2) * b + kap)));       // Gf of leaf j+1
-                if (kap == b - 1) {
-                    int s = a.sep[j];
-                    cplx vs;
-                    if (a.mode == 2) vs = a.vin[s];
-                    else {
-                        vs = ldcg(a.u + (size_t)(m - 1) * n + s);
-                        if (a.mode == 1 && m < n) {
-                            cplx cp = cmul(cmul(hp_rowfac(a, m), a.is1t[2 * (s + 1)]), sgn);
-                            vs = cfma(cp, ldcg(a.u + (size_t)m * n + s), vs);
-                        }
-                    }
-                    acc = cadd(acc, vs);
+                const cplx* pa = slot + a.oGR + ((size_t)j * 2 + 1) * b + kap;          // Gl of leaf j
+                const cplx* pc = slot + a.oGR + ((size_t)(j + 1) * 2) * b + kap;        // Gf of leaf j+1
+                const cplx* pv = slot + a.oVS + j;
+                const bool need_v = kap == b - 1;
+                cplx va, vc, vs = cmake(0.0, 0.0);
+                unsigned int spins = 0;
+                for (;;) {
+                    bool ok = xtry(pa, va);
+                    ok = xtry(pc, vc) && ok;
+                    if (need_v) ok = xtry(pv, vs) && ok;
+                    if (ok) break;
+                    if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); break; }
+                    if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) break;
                 }
-                rho[e] = acc;
+                rho[e] = csub(vs, cadd(va, vc));
             }
         }
         __syncthreads();
-        for (int rr = warp; rr < nrows; rr += nwarps) {      // separator rows first: they are on the critical path
-            cplx acc = cmake(0.0, 0.0);
-            const cplx* nr = Np + (size_t)rr * NSP;
-#pragma unroll 4
-            for (int e = lane; e < NS; e += 32) acc = cfma(nr[e], rho[e], acc);
-            acc = hp_warp_sum2(acc);
-            if (lane == 0) { a.xs[row0 + rr] = acc; xrow[rr] = acc; }
-        }
-        for (int cc = warp; cc < ncols; cc += nwarps) {
-            cplx acc = cmake(0.0, 0.0);
-            const cplx* wr = Wp + (size_t)cc * QP;
-#pragma unroll 4
-            for (int c = lane; c < q; c += 32) acc = cfma(wr[c], v_leaf[c], acc);
-            acc = hp_warp_sum2(acc);
-            if (lane == 0) y0[cc] = acc;
-        }
-        __syncthreads();
         HP_TICK(3);
-        hp_grid_barrier(a.bar, target, G);
+        for (int rr = warp; rr < nrows; rr += nwarps) {      // separator rows first: they are on the critical path
+            cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
+            const cplx* nr = Np + (size_t)rr * NSP;
+            int e = lane;
+            for (; e + 32 < NS; e += 64) { acc = cfma(nr[e], rho[e], acc); acc2 = cfma(nr[e + 32], rho[e + 32], acc2); }
+            if (e < NS) acc = cfma(nr[e], rho[e], acc);
+            acc = hp_warp_sum2(cadd(acc, acc2));
+            if (lane == 0) { xput(slot + a.oXS + row0 + rr, acc); xrow[rr] = acc; }
+        }
+        for (int cc = oct; cc < ncols; cc += nocts) {
+            cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
+            const cplx* wr = Wp + (size_t)cc * QP;
+            int c = lane8;
+            for (; c + 8 < q; c += 16) { acc = cfma(wr[c], v_leaf[c], acc); acc2 = cfma(wr[c + 8], v_leaf[c + 8], acc2); }
+            if (c < q) acc = cfma(wr[c], v_leaf[c], acc);
+            acc = hp_oct_sum2(cadd(acc, acc2));
+            if (lane8 == 0) y0[cc] = acc;
+        }
         HP_TICK(4);
         // ---- S3
         if (tid < 2 * b) {
             int side = tid / b, kap = tid - side * b;
             int j = l - 1 + side;
-            xlr[tid] = (j >= 0 && j < P - 1) ? ldcg(a.xs + (size_t)j * b + kap) : cmake(0.0, 0.0);
+            xlr[tid] = (j >= 0 && j < P - 1) ? xget(slot + a.oXS + (size_t)j * b + kap, abort_flag) : cmake(0.0, 0.0);
+        }
+        __syncthreads();
+        HP_TICK(5);
+        // correction: warp w takes the interface components kap = w, w+8, ...; lanes run over the columns
+        for (int cc = lane; cc < ncols; cc += 32) {
+            cplx acc = cmake(0.0, 0.0);
+            for (int kap = warp; kap < 2 * b; kap += nwarps) acc = cfma(Gp[(size_t)kap * CW + cc], xlr[kap], acc);
+            ypart[(size_t)warp * CW + cc] = acc;
         }
         __syncthreads();
         if (tid < ncols) {
             int c = c0 + tid;
             cplx y = y0[tid];
-#pragma unroll 4
-            for (int kap = 0; kap < 2 * b; ++kap) y = cfms(Gp[(size_t)kap * CW + tid], xlr[kap], y);
+#pragma unroll
+            for (int w = 0; w < HP_SWEEP_THREADS / 32; ++w) y = csub(y, ypart[(size_t)w * CW + tid]);
             if (a.mode == 2) {
                 a.yout[c] = y;
             } else if (a.mode == 0) {
@@ -321,19 +377,27 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
                 }
             }
         }
-        // separator columns: the CTA that computed row (j, b-1) of x_S owns the update of column sep[j]
+        // separator columns: y_s = x_s[b-1]; the input value of the next strip goes to the next slot
         if (sep_col >= 0) {
             cplx y = xrow[tid];
             if (a.mode == 2) a.yout[sep_col] = y;
             else if (a.mode == 0) {
                 cplx cp = cmul(hp_rowfac(a, m), a.is1t[2 * (sep_col + 1)]);
-                a.u[(size_t)m * n + sep_col] = cfms(cp, y, usep);
+                cplx un = cfms(cp, y, usep);
+                a.u[(size_t)m * n + sep_col] = un;
+                if (more) xput(slot_next + a.oVS + sep_j, un);
             } else {
-                a.u[(size_t)(m - 1) * n + sep_col] = a.diag_mode == 0 ? csub(usep, y) : y;
+                cplx un = a.diag_mode == 0 ? csub(usbase, y) : y;
+                a.u[(size_t)(m - 1) * n + sep_col] = un;
+                if (more) {
+                    cplx cp = cmul(cmul(hp_rowfac(a, mn), a.is1t[2 * (sep_col + 1)]), sgn);
+                    usbase = usep;
+                    xput(slot_next + a.oVS + sep_j, cfma(cp, un, usep));
+                }
             }
         }
         __syncthreads();
-        HP_TICK(5);
+        HP_TICK(6);
         if (TMA && tid == 0) {
             // every thread is done with this stage: refill it with the packet two strips ahead
             if (it + 2 < nsteps) {
@@ -347,6 +411,11 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
                 const char* src = (const char*)(pk_base + (size_t)(m + 3 * step - a.m_lo) * strip_stride);
                 for (unsigned int o = 0; o < pk_bytes; o += HP_BULK_CHUNK) bulk_prefetch_l2(src + o, min(HP_BULK_CHUNK, pk_bytes - o));
             }
+        }
+        if ((it & 63) == 63) {                 // a runaway spin somewhere: every CTA leaves within 64 strips
+            if (tid == 0) s_abort = *((volatile unsigned int*)abort_flag);
+            __syncthreads();
+            if (s_abort) break;
         }
     }
     if (a.dbg && tid == 0)
@@ -363,33 +432,47 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
         hp_set_error("sweep: strips %d..%d requested, solver holds %d..%d", lo, hi, s->m_lo, s->m_hi);
         return 1;
     }
+    const HpLayout& L = s->lay;
     HpSweepArgs a;
     a.n = s->n; a.b = s->b; a.lay = s->lay;
     a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
     a.packets = s->packets; a.m_lo = s->m_lo;
     a.mode = mode; a.m_from = m_from; a.m_to = m_to; a.diag_mode = diag_mode;
     a.u = u; a.vin = vin; a.yout = yout;
-    a.vbuf = s->vbuf; a.gparts = s->gparts; a.gred = s->gred; a.xs = s->xs; a.bar = s->bar;
+    a.xch = s->xch; a.bar = s->bar;
+    a.oGP = (size_t)s->n; a.oGR = a.oGP + (size_t)L.G * 2 * s->b; a.oXS = a.oGR + (size_t)L.P * 2 * s->b;
+    a.oVS = a.oXS + L.NSP; a.slot_stride = a.oVS + L.P;
     a.s2t = s->s2t; a.is1t = s->is1t;
     a.ih2 = 1.0 / (s->pml.h * s->pml.h);
     a.dbg = s->dbg;
-    const HpLayout& L = s->lay;
-    size_t small = sizeof(cplx) * ((size_t)2 * L.CW + L.QP + L.NSP + 4 * s->b + L.NR + 1) + 2 * sizeof(unsigned long long);
+    size_t small = sizeof(cplx) * ((size_t)(2 + HP_SWEEP_THREADS / 32) * L.CW + L.QP + L.NSP + 4 * s->b + L.NR + 1) +
+                   2 * sizeof(unsigned long long);
     size_t stage = (L.PK * sizeof(cplx) + 127) & ~(size_t)127;
     int max_smem = 0, dev = 0;
     HP_CUDA(cudaGetDevice(&dev));
     HP_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     bool tma = s->sweep_variant != 1 && 2 * stage + small + 1024 <= (size_t)max_smem;
     size_t smem = small + (tma ? 2 * stage : 0);
+    if (smem + 1024 > (size_t)max_smem) { hp_set_error("sweep: %zu bytes of shared memory needed, %d available", smem, max_smem); return 1; }
     const void* fn = tma ? (const void*)hp_sweep_kernel<true> : (const void*)hp_sweep_kernel<false>;
     if (smem > 48 * 1024) HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int) * (4 + L.P), st));
+    // the exchange ring starts all-sentinel (0xFF bytes); bar[1] = abort flag
+    HP_CUDA(cudaMemsetAsync(s->xch, 0xFF, sizeof(cplx) * HP_RING * a.slot_stride, st));
     void* args[] = {&a};
     hp_count_launch();
     hp_profile_begin(s, st);
     HP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.G), dim3(HP_SWEEP_THREADS), args, smem, st));
     hp_profile_end(s, st, (int64_t)(hi - lo + 1) * ((int64_t)L.G * L.PK + 3 * (int64_t)s->n) * (int64_t)sizeof(cplx));
     return 0;
+}
+
+// 0 = fine; 1 = a CTA of a sweep kernel gave up waiting for exchange data (synchronises the device)
+extern "C" int hp_sweep_status(hp_solver* s) {
+    if (!s || !s->bar) return 0;
+    unsigned int v[2] = {0, 0};
+    if (cudaDeviceSynchronize() != cudaSuccess) return 2;
+    if (cudaMemcpy(v, s->bar, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 2;
+    return v[1] ? 1 : 0;
 }
 
 extern "C" int hp_sweep_forward(hp_solver* s, double* u_dev, int m_from, int m_to, void* stream) {

@@ -117,6 +117,10 @@ class HelmholtzSolver:
         _lib.check(self.lib.hp_set_sweep_variant(self.handle, int(variant)), "hp_set_sweep_variant")
         return self
 
+    def sweep_status(self):
+        """0 = fine (synchronises the device)."""
+        return int(self.lib.hp_sweep_status(self.handle))
+
     @property
     def precond_bytes(self):
         return int(self.lib.hp_precond_bytes(self.handle))

@@ -70,6 +70,8 @@ int64_t hp_precond_bytes(hp_solver* s);
 double hp_precond_setup_ms(hp_solver* s);
 /* sweep kernel variant: 0 = automatic (TMA-staged packets when two fit in shared memory), 1 = direct loads */
 int hp_set_sweep_variant(hp_solver* s, int variant);
+/* 0 = fine; 1 = a sweep kernel gave up waiting for data from another CTA (a bug, never expected); synchronises */
+int hp_sweep_status(hp_solver* s);
 
 /* The three stages of algo2_4 (code.py:356-385), operating in place on the field u_dev (n*n complex):
  *   hp_front_begin   : T_F u_F = H_F^{-1} u_F kept aside, u_{b+1} -= A_{b+1,F} T_F u_F        (:364-365)

@@ -105,6 +105,7 @@ def test_strip_apply_vs_oracle(hp, n, b, P, K):
             v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
             y = s.strip_apply(m, dev(v))
             assert relerr(y, Pc.T(m, v)) < 1e-12
+    assert s.sweep_status() == 0
     s.close()
 
 
@@ -183,4 +184,5 @@ def test_medium_preconditioner_vs_oracle(hp):
     assert relerr(hp.algo2_4(f, b, n, s), ref) < 1e-12
     s.set_sweep_variant(1)
     assert relerr(hp.algo2_4(f, b, n, s), ref) < 1e-12
+    assert s.sweep_status() == 0
     s.close()
