@@ -27,7 +27,7 @@
 
 #define HP_SWEEP_THREADS 256
 #define HP_RING 4
-#define HP_SPIN_LIMIT (1u << 24)
+#define HP_SPIN_LIMIT (1u << 21)
 
 struct HpSweepArgs {
     int n, b;
@@ -114,11 +114,13 @@ __device__ __forceinline__ cplx hp_warp_sum2(cplx v) {
     return v;
 }
 // sum over the aligned group of 8 lanes a thread belongs to
+// (only that octet has to take part: the loops over octets are not warp uniform)
 __device__ __forceinline__ cplx hp_oct_sum2(cplx v) {
+    const unsigned int mask = 0xFFu << (threadIdx.x & 24);
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
-        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
-        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+        v.x += __shfl_xor_sync(mask, v.x, o);
+        v.y += __shfl_xor_sync(mask, v.y, o);
     }
     return v;
 }
