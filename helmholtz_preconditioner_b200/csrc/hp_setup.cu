@@ -128,8 +128,9 @@ __global__ void __launch_bounds__(128) hp_sep_rows_kernel(HpSetupArgs a) {
 static void hp_fill_layout(HpLayout& L, int n, int b, int P, int K) {
     int inner = n - (P - 1);
     L.P = P; L.K = K; L.G = P * K;
-    L.QP = (inner + P - 1) / P;
-    L.CW = (L.QP + K - 1) / K;
+    int qmax = (inner + P - 1) / P;
+    L.QP = qmax | 1;                       // row strides are odd numbers of 16-byte entries: a quarter warp that
+    L.CW = ((qmax + K - 1) / K) | 1;       // reads 8 consecutive rows of Wp / Gp in shared memory hits 8 bank groups
     L.NS = b * (P - 1);
     L.NSP = L.NS > 0 ? L.NS : 1;
     L.NR = L.NS > 0 ? (L.NS + L.G - 1) / L.G : 0;

@@ -113,18 +113,6 @@ __device__ __forceinline__ cplx hp_warp_sum2(cplx v) {
     }
     return v;
 }
-// sum over the aligned group of 8 lanes a thread belongs to
-// (only that octet has to take part: the loops over octets are not warp uniform)
-__device__ __forceinline__ cplx hp_oct_sum2(cplx v) {
-    const unsigned int mask = 0xFFu << (threadIdx.x & 24);
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-        v.x += __shfl_xor_sync(mask, v.x, o);
-        v.y += __shfl_xor_sync(mask, v.y, o);
-    }
-    return v;
-}
-
 // coupling A_{j+1,j}[c] = c3 of grid row j+1 = s2((j+.5)h)/(h^2 s1(ih)) = A_{j,j+1}[c] (c4 of row j); rowfac is
 // the x2 part for the pair (j, j+1), 1-based j
 __device__ __forceinline__ cplx hp_rowfac(const HpSweepArgs& a, int j) { return cscale(a.ih2, a.s2t[2 * j + 1]); }
@@ -138,7 +126,6 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
     const int NS = a.lay.NS, NSP = a.lay.NSP, NR = a.lay.NR;
     const int g = blockIdx.x, l = g / K, k = g % K;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = HP_SWEEP_THREADS / 32;
-    const int oct = tid >> 3, lane8 = tid & 7, nocts = HP_SWEEP_THREADS / 8;
     const int q = a.leaf_q[l], ls = a.leaf_start[l];
     const int lc0 = (q * k) / K, lc1 = (q * (k + 1)) / K, ncols = lc1 - lc0, c0 = ls + lc0;
     const int row0 = g * NR, nrows = max(0, min(NR, NS - row0));
@@ -149,12 +136,13 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
     cplx* small = reinterpret_cast<cplx*>(smem_raw + (TMA ? 2 * stage_bytes : 0));
     cplx* v_own = small;                // [CW]
     cplx* v_leaf = v_own + CW;          // [QP]
-    cplx* y0 = v_leaf + QP;             // [CW]
-    cplx* rho = y0 + CW;                // [NSP]
+    cplx* rho = v_leaf + QP;            // [NSP]
     cplx* xlr = rho + NSP;              // [2b]  x_left, x_right
     cplx* xrow = xlr + 2 * b;           // [NR+1] own rows of x_S
-    cplx* gp_s = xrow + NR + 1;         // [2b]  own partial g
-    cplx* ypart = gp_s + 2 * b;         // [8][CW] partial sums of the S3 correction
+    cplx* gpw = xrow + NR + 1;          // [8][2b]  per-warp partial g
+    cplx* nred = gpw + (size_t)nwarps * 2 * b;      // [8][4]   per-warp partial separator rows
+    cplx* y0w = nred + nwarps * 4;      // [8][CW]  per-warp partial leaf products
+    cplx* ypart = y0w + (size_t)nwarps * CW;         // [8][CW]  per-warp partial corrections
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ypart + (size_t)nwarps * CW);   // [2]
 
     __shared__ unsigned int s_abort;
@@ -265,18 +253,23 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
         if (a.dbg && tid == 0) tprev = clock64();
         if (TMA) mbar_wait(&mbar[it & 1], (it >> 1) & 1);
         HP_TICK(0);
-        // ---- S1: publish own columns, partial interface data
+        // ---- S1: publish own columns; g = Gp v_own with lanes over the 2b interface components (rows of Gp,
+        //      odd row stride -> conflict-free) and warps over column subsets (v_own is a broadcast read)
         if (K > 1 && tid < ncols) xput(slot + c0 + tid, v_own[tid]);
-        for (int kap = oct; kap < 2 * b; kap += nocts) {
+        for (int kap = lane; kap < 2 * b; kap += 32) {
             cplx acc = cmake(0.0, 0.0);
             const cplx* gr = Gp + (size_t)kap * CW;
-            for (int cc = lane8; cc < ncols; cc += 8) acc = cfma(gr[cc], v_own[cc], acc);
-            acc = hp_oct_sum2(acc);
-            if (lane8 == 0) {
-                if (K == 1) xput(slot + a.oGR + (size_t)l * 2 * b + kap, acc);
-                else if (k == 0) gp_s[kap] = acc;
-                else xput(slot + a.oGP + (size_t)g * 2 * b + kap, acc);
-            }
+            for (int cc = warp; cc < ncols; cc += nwarps) acc = cfma(gr[cc], v_own[cc], acc);
+            gpw[warp * 2 * b + kap] = acc;
+        }
+        __syncthreads();
+        if (tid < 2 * b) {
+            cplx acc = gpw[tid];
+#pragma unroll
+            for (int w = 1; w < HP_SWEEP_THREADS / 32; ++w) acc = cadd(acc, gpw[w * 2 * b + tid]);
+            if (K == 1) xput(slot + a.oGR + (size_t)l * 2 * b + tid, acc);
+            else if (k > 0) xput(slot + a.oGP + (size_t)g * 2 * b + tid, acc);
+            else gpw[tid] = acc;          // the leaf's first CTA adds the other parts below (same thread)
         }
         // re-arm what this CTA wrote two strips ago (slot it+2 = it-2 mod 4)
         if (K > 1 && tid < ncols) xarm(slot_arm + c0 + tid);
@@ -287,13 +280,10 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
         if (tid < nrows) xarm(slot_arm + a.oXS + row0 + tid);
         if (sep_col >= 0) xarm(slot_arm + a.oVS + sep_j);
         HP_TICK(1);
-        if (K > 1 && k == 0) {
-            __syncthreads();
-            if (tid < 2 * b) {
-                cplx acc = gp_s[tid];
-                for (int kk = 1; kk < K; ++kk) acc = cadd(acc, xget(slot + a.oGP + (size_t)(g + kk) * 2 * b + tid, abort_flag));
-                xput(slot + a.oGR + (size_t)l * 2 * b + tid, acc);
-            }
+        if (K > 1 && k == 0 && tid < 2 * b) {
+            cplx acc = gpw[tid];
+            for (int kk = 1; kk < K; ++kk) acc = cadd(acc, xget(slot + a.oGP + (size_t)(g + kk) * 2 * b + tid, abort_flag));
+            xput(slot + a.oGR + (size_t)l * 2 * b + tid, acc);
         }
         HP_TICK(2);
         // ---- S2
@@ -321,23 +311,41 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
         }
         __syncthreads();
         HP_TICK(3);
-        for (int rr = warp; rr < nrows; rr += nwarps) {      // separator rows first: they are on the critical path
-            cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
-            const cplx* nr = Np + (size_t)rr * NSP;
-            int e = lane;
-            for (; e + 32 < NS; e += 64) { acc = cfma(nr[e], rho[e], acc); acc2 = cfma(nr[e + 32], rho[e + 32], acc2); }
-            if (e < NS) acc = cfma(nr[e], rho[e], acc);
-            acc = hp_warp_sum2(cadd(acc, acc2));
-            if (lane == 0) { xput(slot + a.oXS + row0 + rr, acc); xrow[rr] = acc; }
+        // separator rows first (they are on the critical path): threads over the columns of N, 4 rows at a time
+        for (int r0 = 0; r0 < nrows; r0 += 4) {
+            cplx acc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = cmake(0.0, 0.0);
+            for (int e = tid; e < NS; e += HP_SWEEP_THREADS) {
+                cplx r = rho[e];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (r0 + i < nrows) acc[i] = cfma(Np[(size_t)(r0 + i) * NSP + e], r, acc[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = hp_warp_sum2(acc[i]);
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nred[warp * 4 + i] = acc[i];
+            }
+            __syncthreads();
+            if (tid < 4 && r0 + tid < nrows) {
+                cplx t = nred[tid];
+#pragma unroll
+                for (int w = 1; w < HP_SWEEP_THREADS / 32; ++w) t = cadd(t, nred[w * 4 + tid]);
+                xput(slot + a.oXS + row0 + r0 + tid, t);
+                xrow[r0 + tid] = t;
+            }
+            if (r0 + 4 < nrows) __syncthreads();
         }
-        for (int cc = oct; cc < ncols; cc += nocts) {
+        // leaf product: lanes over the rows of Wp (odd row stride -> conflict-free), warps over column subsets
+        for (int cc = lane; cc < ncols; cc += 32) {
             cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
             const cplx* wr = Wp + (size_t)cc * QP;
-            int c = lane8;
-            for (; c + 8 < q; c += 16) { acc = cfma(wr[c], v_leaf[c], acc); acc2 = cfma(wr[c + 8], v_leaf[c + 8], acc2); }
+            int c = warp;
+            for (; c + nwarps < q; c += 2 * nwarps) { acc = cfma(wr[c], v_leaf[c], acc); acc2 = cfma(wr[c + nwarps], v_leaf[c + nwarps], acc2); }
             if (c < q) acc = cfma(wr[c], v_leaf[c], acc);
-            acc = hp_oct_sum2(cadd(acc, acc2));
-            if (lane8 == 0) y0[cc] = acc;
+            y0w[(size_t)warp * CW + cc] = cadd(acc, acc2);
         }
         HP_TICK(4);
         // ---- S3
@@ -357,9 +365,9 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
         __syncthreads();
         if (tid < ncols) {
             int c = c0 + tid;
-            cplx y = y0[tid];
+            cplx y = cmake(0.0, 0.0);
 #pragma unroll
-            for (int w = 0; w < HP_SWEEP_THREADS / 32; ++w) y = csub(y, ypart[(size_t)w * CW + tid]);
+            for (int w = 0; w < HP_SWEEP_THREADS / 32; ++w) y = cadd(y, csub(y0w[(size_t)w * CW + tid], ypart[(size_t)w * CW + tid]));
             if (a.mode == 2) {
                 a.yout[c] = y;
             } else if (a.mode == 0) {
@@ -447,7 +455,8 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     a.s2t = s->s2t; a.is1t = s->is1t;
     a.ih2 = 1.0 / (s->pml.h * s->pml.h);
     a.dbg = s->dbg;
-    size_t small = sizeof(cplx) * ((size_t)(2 + HP_SWEEP_THREADS / 32) * L.CW + L.QP + L.NSP + 4 * s->b + L.NR + 1) +
+    const int nw = HP_SWEEP_THREADS / 32;
+    size_t small = sizeof(cplx) * ((size_t)(1 + 2 * nw) * L.CW + L.QP + L.NSP + 2 * s->b + L.NR + 1 + (size_t)nw * 2 * s->b + nw * 4) +
                    2 * sizeof(unsigned long long);
     size_t stage = (L.PK * sizeof(cplx) + 127) & ~(size_t)127;
     int max_smem = 0, dev = 0;
