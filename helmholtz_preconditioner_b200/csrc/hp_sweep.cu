@@ -25,7 +25,9 @@
 // them from global memory behind an L2 prefetch.
 #include "hp_internal.cuh"
 
-#define HP_SWEEP_THREADS 256
+#ifndef HP_SWEEP_THREADS
+#define HP_SWEEP_THREADS 512
+#endif
 #define HP_RING 4
 #define HP_SPIN_LIMIT (1u << 21)
 
@@ -186,6 +188,10 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
         int j = row / b;
         if (row - j * b == b - 1) { sep_j = j; sep_col = a.sep[j]; }
     }
+    const cplx cis1 = tid < ncols ? a.is1t[2 * (c0 + tid + 1)] : cmake(0.0, 0.0);       // 1/s1 of the own column
+    const cplx cis1s = sep_col >= 0 ? a.is1t[2 * (sep_col + 1)] : cmake(0.0, 0.0);      // ... of the own separator column
+    // rho entry of this thread (entries beyond the first HP_SWEEP_THREADS are indexed in the loop)
+    const int rho_j = tid < NS ? tid / b : 0, rho_kap = tid < NS ? tid - (tid / b) * b : 0;
     // input of the first strip; ubase = the u value the epilogue of this strip combines with y
     cplx ubase = cmake(0.0, 0.0), usbase = cmake(0.0, 0.0);
     if (tid < ncols) {
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
             ubase = ldcg(a.u + (size_t)(m - 1) * n + c);
             v = ubase;
             if (m < n) {
-                cplx cp = cmul(cmul(hp_rowfac(a, m), a.is1t[2 * (c + 1)]), sgn);
+                cplx cp = cmul(cmul(hp_rowfac(a, m), cis1), sgn);
                 v = cfma(cp, ldcg(a.u + (size_t)m * n + c), v);
             }
         }
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
             usbase = ldcg(a.u + (size_t)(m - 1) * n + sep_col);
             v = usbase;
             if (m < n) {
-                cplx cp = cmul(cmul(hp_rowfac(a, m), a.is1t[2 * (sep_col + 1)]), sgn);
+                cplx cp = cmul(cmul(hp_rowfac(a, m), cis1s), sgn);
                 v = cfma(cp, ldcg(a.u + (size_t)m * n + sep_col), v);
             }
         }
@@ -239,6 +245,8 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
         const cplx* Wp = pk;
         const cplx* Gp = pk + a.lay.offG;
         const cplx* Np = pk + a.lay.offN;
+        // coupling between grid rows for this strip's epilogue (forward: rows m, m+1; backward: next strip's pair)
+        const cplx rfac = hp_rowfac(a, a.mode == 1 ? mn : m);
         // early loads of the u values the epilogue needs (written by no other CTA)
         cplx upre = cmake(0.0, 0.0), usep = cmake(0.0, 0.0);
         if (tid < ncols) {
@@ -291,7 +299,8 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
             v_leaf[c] = (c >= lc0 && c < lc1) ? v_own[c - lc0] : xget(slot + ls + c, abort_flag);
         if (nrows > 0) {
             for (int e = tid; e < NS; e += HP_SWEEP_THREADS) {
-                int j = e / b, kap = e - j * b;
+                int j = rho_j, kap = rho_kap;
+                if (e != tid) { j = e / b; kap = e - j * b; }
                 const cplx* pa = slot + a.oGR + ((size_t)j * 2 + 1) * b + kap;          // Gl of leaf j
                 const cplx* pc = slot + a.oGR + ((size_t)(j + 1) * 2) * b + kap;        // Gf of leaf j+1
                 const cplx* pv = slot + a.oVS + j;
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
                 a.yout[c] = y;
             } else if (a.mode == 0) {
                 // u_{m+1} -= c3(row m+1) y ; the result is the input of strip m+1
-                cplx cp = cmul(hp_rowfac(a, m), a.is1t[2 * (c + 1)]);
+                cplx cp = cmul(rfac, cis1);
                 cplx un = cfms(cp, y, upre);
                 a.u[(size_t)m * n + c] = un;
                 v_own[tid] = un;
@@ -381,7 +390,7 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
                 a.u[(size_t)(m - 1) * n + c] = un;
                 if (more) {
                     // input of strip m-1: u_{m-1} (+/-) c4(row m-1) u_m
-                    cplx cp = cmul(cmul(hp_rowfac(a, mn), a.is1t[2 * (c + 1)]), sgn);
+                    cplx cp = cmul(cmul(rfac, cis1), sgn);
                     ubase = upre;
                     v_own[tid] = cfma(cp, un, upre);
                 }
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
             cplx y = xrow[tid];
             if (a.mode == 2) a.yout[sep_col] = y;
             else if (a.mode == 0) {
-                cplx cp = cmul(hp_rowfac(a, m), a.is1t[2 * (sep_col + 1)]);
+                cplx cp = cmul(rfac, cis1s);
                 cplx un = cfms(cp, y, usep);
                 a.u[(size_t)m * n + sep_col] = un;
                 if (more) xput(slot_next + a.oVS + sep_j, un);
@@ -400,7 +409,7 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
                 cplx un = a.diag_mode == 0 ? csub(usbase, y) : y;
                 a.u[(size_t)(m - 1) * n + sep_col] = un;
                 if (more) {
-                    cplx cp = cmul(cmul(hp_rowfac(a, mn), a.is1t[2 * (sep_col + 1)]), sgn);
+                    cplx cp = cmul(cmul(rfac, cis1s), sgn);
                     usbase = usep;
                     xput(slot_next + a.oVS + sep_j, cfma(cp, un, usep));
                 }
