@@ -57,14 +57,14 @@ __device__ __forceinline__ cplx ldcg(const cplx* p) {
 // ---- self-validating exchange words -----------------------------------------------------------------
 #define HP_SENTINEL 0xFFFFFFFFFFFFFFFFull
 __device__ __forceinline__ void xput(cplx* p, cplx v) {
-    asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 __device__ __forceinline__ void xarm(cplx* p) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(p), "l"(HP_SENTINEL) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %1};" ::"l"(p), "l"(HP_SENTINEL) : "memory");
 }
 __device__ __forceinline__ bool xtry(const cplx* p, cplx& v) {
     unsigned long long lo, hi;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
     v.x = __longlong_as_double((long long)lo);
     v.y = __longlong_as_double((long long)hi);
     return lo != HP_SENTINEL && hi != HP_SENTINEL;
@@ -295,6 +295,14 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
         }
         HP_TICK(2);
         // ---- S2
+        // Wait on one representative word per producer (the last one it writes) with a few threads only, so
+        // that the spinning does not flood L2; the bulk reads below still validate every word they take.
+        if (K > 1 && tid < K && tid != k) {
+            int qk1 = (q * (tid + 1)) / K;                 // last column of part tid
+            if (qk1 > (q * tid) / K) xget(slot + ls + qk1 - 1, abort_flag);
+        }
+        if (nrows > 0 && tid >= 32 && tid < 32 + P) xget(slot + a.oGR + (size_t)(tid - 32) * 2 * b + 2 * b - 1, abort_flag);
+        __syncthreads();
         for (int c = tid; c < q; c += HP_SWEEP_THREADS)
             v_leaf[c] = (c >= lc0 && c < lc1) ? v_own[c - lc0] : xget(slot + ls + c, abort_flag);
         if (nrows > 0) {
