@@ -26,7 +26,7 @@
 #include "hp_internal.cuh"
 
 #ifndef HP_SWEEP_THREADS
-#define HP_SWEEP_THREADS 512
+#define HP_SWEEP_THREADS 256
 #endif
 #define HP_RING 4
 #define HP_SPIN_LIMIT (1u << 21)
@@ -121,16 +121,6 @@ __device__ __forceinline__ cplx hp_rowfac(const HpSweepArgs& a, int j) { return 
 
 #define HP_BULK_CHUNK 32768u
 
-#define HP_CPL 4     // columns per lane of the chain warp: parts up to 128 columns wide
-#define HP_KPL 2     // interface components per lane: 2b <= 64
-
-// Warp roles inside a CTA, per strip t (all warps share S2; "tail" is warp 0 only):
-//   S2   all warps : wait for / read V (leaf peers), GR (all leaves), VS  -> v_leaf, rho          | sync a
-//        warps 1.. : separator rows x_S = Np rho -> publish XS           (critical path first)
-//        all warps : partial leaf products y0w = Wp v_leaf                                         | sync b
-//   tail warp 0    : wait XS -> y = y0 - Gcorr^T x -> epilogue (u, next input v) -> publish V ->
-//                    g = Gp(t+1) v -> publish GP / reduce -> GR   (S3 of strip t fused with S1 of strip t+1)
-//        the other warps go straight to the S2 of strip t+1 and wait there.
 template <bool TMA>
 __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -144,18 +134,20 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
     const unsigned int pk_bytes = (unsigned int)(a.lay.PK * sizeof(cplx));
     const size_t stage_bytes = ((size_t)pk_bytes + 127) & ~(size_t)127;
     unsigned int* abort_flag = a.bar + 1;
-    const bool chain = warp == 0;
 
     cplx* small = reinterpret_cast<cplx*>(smem_raw + (TMA ? 2 * stage_bytes : 0));
-    cplx* v_own = small;                // [CW]   chain warp scratch: the next input on the own columns
+    cplx* v_own = small;                // [CW]
     cplx* v_leaf = v_own + CW;          // [QP]
     cplx* rho = v_leaf + QP;            // [NSP]
     cplx* xlr = rho + NSP;              // [2b]  x_left, x_right
     cplx* xrow = xlr + 2 * b;           // [NR+1] own rows of x_S
-    cplx* y0w = xrow + NR + 1;          // [nwarps][CW]  per-warp partial leaf products
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(y0w + (size_t)nwarps * CW);   // [2]
-    __shared__ unsigned int s_abort;
+    cplx* gpw = xrow + NR + 1;          // [8][2b]  per-warp partial g
+    cplx* nred = gpw + (size_t)nwarps * 2 * b;      // [8][4]   per-warp partial separator rows
+    cplx* y0w = nred + nwarps * 4;      // [8][CW]  per-warp partial leaf products
+    cplx* ypart = y0w + (size_t)nwarps * CW;         // [8][CW]  per-warp partial corrections
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ypart + (size_t)nwarps * CW);   // [2]
 
+    __shared__ unsigned int s_abort;
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
 #define HP_TICK(i) do { if (a.dbg && tid == 0) { long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
     const int step = a.mode == 1 ? -1 : 1;
@@ -188,132 +180,123 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
             }
         }
     }
-    auto packet = [&](int it_, int m_) -> const cplx* {
-        return TMA ? reinterpret_cast<const cplx*>(smem_raw + (it_ & 1) * stage_bytes)
-                   : pk_base + (size_t)(m_ - a.m_lo) * strip_stride;
-    };
 
-    // the separator column a chain-warp lane owns (the CTA that computes row (j, b-1) of x_S updates column sep[j])
+    // the separator column this thread owns (the CTA that computes row (j, b-1) of x_S updates column sep[j])
     int sep_j = -1, sep_col = -1;
     if (tid < nrows) {
         int row = row0 + tid;
         int j = row / b;
         if (row - j * b == b - 1) { sep_j = j; sep_col = a.sep[j]; }
     }
-    const cplx cis1s = sep_col >= 0 ? a.is1t[2 * (sep_col + 1)] : cmake(0.0, 0.0);
-    cplx cis1[HP_CPL], ubase[HP_CPL], usbase = cmake(0.0, 0.0);
-#pragma unroll
-    for (int i = 0; i < HP_CPL; ++i) {
-        int cc = lane + 32 * i;
-        cis1[i] = (chain && cc < ncols) ? a.is1t[2 * (c0 + cc + 1)] : cmake(0.0, 0.0);     // 1/s1 of the own columns
-        ubase[i] = cmake(0.0, 0.0);
-    }
+    const cplx cis1 = tid < ncols ? a.is1t[2 * (c0 + tid + 1)] : cmake(0.0, 0.0);       // 1/s1 of the own column
+    const cplx cis1s = sep_col >= 0 ? a.is1t[2 * (sep_col + 1)] : cmake(0.0, 0.0);      // ... of the own separator column
     // rho entry of this thread (entries beyond the first HP_SWEEP_THREADS are indexed in the loop)
     const int rho_j = tid < NS ? tid / b : 0, rho_kap = tid < NS ? tid - (tid / b) * b : 0;
-
-    // S1 of a strip: chain warp only.  v_own (smem) holds the input on the own columns; Gp_ the strip's [Gf; Gl].
-    auto s1_publish = [&](cplx* slot_, const cplx* Gp_) {
-#pragma unroll
-        for (int i = 0; i < HP_KPL; ++i) {
-            int kap = lane + 32 * i;
-            if (kap < 2 * b) {
-                cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
-                const cplx* gr = Gp_ + (size_t)kap * CW;
-                int cc = 0;
-                for (; cc + 1 < ncols; cc += 2) { acc = cfma(gr[cc], v_own[cc], acc); acc2 = cfma(gr[cc + 1], v_own[cc + 1], acc2); }
-                if (cc < ncols) acc = cfma(gr[cc], v_own[cc], acc);
-                acc = cadd(acc, acc2);
-                if (K == 1) xput(slot_ + a.oGR + (size_t)l * 2 * b + kap, acc);
-                else if (k > 0) xput(slot_ + a.oGP + (size_t)g * 2 * b + kap, acc);
-                else {
-                    for (int kk = 1; kk < K; ++kk) acc = cadd(acc, xget(slot_ + a.oGP + (size_t)(g + kk) * 2 * b + kap, abort_flag));
-                    xput(slot_ + a.oGR + (size_t)l * 2 * b + kap, acc);
-                }
+    // input of the first strip; ubase = the u value the epilogue of this strip combines with y
+    cplx ubase = cmake(0.0, 0.0), usbase = cmake(0.0, 0.0);
+    if (tid < ncols) {
+        int c = c0 + tid;
+        cplx v;
+        if (a.mode == 2) v = a.vin[c];
+        else if (a.mode == 0) { v = ldcg(a.u + (size_t)(m - 1) * n + c); }
+        else {
+            ubase = ldcg(a.u + (size_t)(m - 1) * n + c);
+            v = ubase;
+            if (m < n) {
+                cplx cp = cmul(cmul(hp_rowfac(a, m), cis1), sgn);
+                v = cfma(cp, ldcg(a.u + (size_t)m * n + c), v);
             }
         }
-    };
-
-    // ---- prologue: input of the first strip, its S1
-    if (chain) {
-#pragma unroll
-        for (int i = 0; i < HP_CPL; ++i) {
-            int cc = lane + 32 * i;
-            if (cc < ncols) {
-                int c = c0 + cc;
-                cplx v;
-                if (a.mode == 2) v = a.vin[c];
-                else if (a.mode == 0) v = ldcg(a.u + (size_t)(m - 1) * n + c);
-                else {
-                    ubase[i] = ldcg(a.u + (size_t)(m - 1) * n + c);
-                    v = ubase[i];
-                    if (m < n) {
-                        cplx cp = cmul(cmul(hp_rowfac(a, m), cis1[i]), sgn);
-                        v = cfma(cp, ldcg(a.u + (size_t)m * n + c), v);
-                    }
-                }
-                v_own[cc] = v;
-                v_leaf[lc0 + cc] = v;
-                if (K > 1) xput(a.xch + c0 + cc, v);             // slot 0
-            }
-        }
-        if (sep_col >= 0) {
-            cplx v;
-            if (a.mode == 2) v = a.vin[sep_col];
-            else if (a.mode == 0) v = ldcg(a.u + (size_t)(m - 1) * n + sep_col);
-            else {
-                usbase = ldcg(a.u + (size_t)(m - 1) * n + sep_col);
-                v = usbase;
-                if (m < n) {
-                    cplx cp = cmul(cmul(hp_rowfac(a, m), cis1s), sgn);
-                    v = cfma(cp, ldcg(a.u + (size_t)m * n + sep_col), v);
-                }
-            }
-            xput(a.xch + a.oVS + sep_j, v);                     // slot 0
-        }
-        __syncwarp();
-        if (TMA) mbar_wait(&mbar[0], 0);
-        s1_publish(a.xch, packet(0, m) + a.lay.offG);
+        v_own[tid] = v;
     }
+    if (sep_col >= 0) {
+        cplx v;
+        if (a.mode == 2) v = a.vin[sep_col];
+        else if (a.mode == 0) v = ldcg(a.u + (size_t)(m - 1) * n + sep_col);
+        else {
+            usbase = ldcg(a.u + (size_t)(m - 1) * n + sep_col);
+            v = usbase;
+            if (m < n) {
+                cplx cp = cmul(cmul(hp_rowfac(a, m), cis1s), sgn);
+                v = cfma(cp, ldcg(a.u + (size_t)m * n + sep_col), v);
+            }
+        }
+        xput(a.xch + a.oVS + sep_j, v);                 // slot 0
+    }
+    __syncthreads();
 
     for (int it = 0; it < nsteps; ++it, m += step) {
         const int mn = m + step;               // next strip
         const bool more = it + 1 < nsteps;
         cplx* slot = a.xch + (size_t)(it & (HP_RING - 1)) * a.slot_stride;
         cplx* slot_next = a.xch + (size_t)((it + 1) & (HP_RING - 1)) * a.slot_stride;
-        cplx* slot_arm = a.xch + (size_t)((it + 3) & (HP_RING - 1)) * a.slot_stride;     // strip it-1: consumed by all
-        const cplx* pk = packet(it, m);
-        if (!TMA && more) {   // pull the next strip's packet towards L2 while this one is processed
-            const char* nx = (const char*)(pk_base + (size_t)(mn - a.m_lo) * strip_stride);
-            for (size_t o = (size_t)tid * 128; o < pk_bytes; o += (size_t)HP_SWEEP_THREADS * 128)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+        cplx* slot_arm = a.xch + (size_t)((it + 2) & (HP_RING - 1)) * a.slot_stride;
+        const cplx* pk;
+        if (TMA) {
+            pk = reinterpret_cast<const cplx*>(smem_raw + (it & 1) * stage_bytes);
+        } else {
+            pk = pk_base + (size_t)(m - a.m_lo) * strip_stride;
+            if (more) {   // pull the next strip's packet towards L2 while this one is processed
+                const char* nx = (const char*)(pk_base + (size_t)(mn - a.m_lo) * strip_stride);
+                for (size_t o = (size_t)tid * 128; o < pk_bytes; o += (size_t)HP_SWEEP_THREADS * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+            }
         }
         const cplx* Wp = pk;
         const cplx* Gp = pk + a.lay.offG;
         const cplx* Np = pk + a.lay.offN;
-        // chain warp: coupling between grid rows and the u values this strip's epilogue needs (written by no other CTA)
-        cplx rfac = cmake(0.0, 0.0), upre[HP_CPL], usep = cmake(0.0, 0.0);
-        if (chain) {
-            rfac = hp_rowfac(a, a.mode == 1 ? mn : m);
-#pragma unroll
-            for (int i = 0; i < HP_CPL; ++i) {
-                int cc = lane + 32 * i;
-                upre[i] = cmake(0.0, 0.0);
-                if (cc < ncols) {
-                    if (a.mode == 0) upre[i] = ldcg(a.u + (size_t)m * n + c0 + cc);
-                    else if (a.mode == 1 && more) upre[i] = ldcg(a.u + (size_t)(mn - 1) * n + c0 + cc);
-                }
-            }
-            if (sep_col >= 0) {
-                if (a.mode == 0) usep = ldcg(a.u + (size_t)m * n + sep_col);
-                else if (a.mode == 1 && more) usep = ldcg(a.u + (size_t)(mn - 1) * n + sep_col);
-            }
+        // coupling between grid rows for this strip's epilogue (forward: rows m, m+1; backward: next strip's pair)
+        const cplx rfac = hp_rowfac(a, a.mode == 1 ? mn : m);
+        // early loads of the u values the epilogue needs (written by no other CTA)
+        cplx upre = cmake(0.0, 0.0), usep = cmake(0.0, 0.0);
+        if (tid < ncols) {
+            int c = c0 + tid;
+            if (a.mode == 0) upre = ldcg(a.u + (size_t)m * n + c);
+            else if (a.mode == 1 && more) upre = ldcg(a.u + (size_t)(mn - 1) * n + c);
+        }
+        if (sep_col >= 0) {
+            if (a.mode == 0) usep = ldcg(a.u + (size_t)m * n + sep_col);
+            else if (a.mode == 1 && more) usep = ldcg(a.u + (size_t)(mn - 1) * n + sep_col);
         }
         if (a.dbg && tid == 0) tprev = clock64();
         if (TMA) mbar_wait(&mbar[it & 1], (it >> 1) & 1);
         HP_TICK(0);
-        // ---- S2: gather v_leaf (peers' columns) and rho
+        // ---- S1: publish own columns; g = Gp v_own with lanes over the 2b interface components (rows of Gp,
+        //      odd row stride -> conflict-free) and warps over column subsets (v_own is a broadcast read)
+        if (K > 1 && tid < ncols) xput(slot + c0 + tid, v_own[tid]);
+        for (int kap = lane; kap < 2 * b; kap += 32) {
+            cplx acc = cmake(0.0, 0.0);
+            const cplx* gr = Gp + (size_t)kap * CW;
+            for (int cc = warp; cc < ncols; cc += nwarps) acc = cfma(gr[cc], v_own[cc], acc);
+            gpw[warp * 2 * b + kap] = acc;
+        }
+        __syncthreads();
+        if (tid < 2 * b) {
+            cplx acc = gpw[tid];
+#pragma unroll
+            for (int w = 1; w < HP_SWEEP_THREADS / 32; ++w) acc = cadd(acc, gpw[w * 2 * b + tid]);
+            if (K == 1) xput(slot + a.oGR + (size_t)l * 2 * b + tid, acc);
+            else if (k > 0) xput(slot + a.oGP + (size_t)g * 2 * b + tid, acc);
+            else gpw[tid] = acc;          // the leaf's first CTA adds the other parts below (same thread)
+        }
+        // re-arm what this CTA wrote two strips ago (slot it+2 = it-2 mod 4)
+        if (K > 1 && tid < ncols) xarm(slot_arm + c0 + tid);
+        if (tid < 2 * b) {
+            if (K > 1 && k > 0) xarm(slot_arm + a.oGP + (size_t)g * 2 * b + tid);
+            if (k == 0) xarm(slot_arm + a.oGR + (size_t)l * 2 * b + tid);
+        }
+        if (tid < nrows) xarm(slot_arm + a.oXS + row0 + tid);
+        if (sep_col >= 0) xarm(slot_arm + a.oVS + sep_j);
+        HP_TICK(1);
+        if (K > 1 && k == 0 && tid < 2 * b) {
+            cplx acc = gpw[tid];
+            for (int kk = 1; kk < K; ++kk) acc = cadd(acc, xget(slot + a.oGP + (size_t)(g + kk) * 2 * b + tid, abort_flag));
+            xput(slot + a.oGR + (size_t)l * 2 * b + tid, acc);
+        }
+        HP_TICK(2);
+        // ---- S2
         for (int c = tid; c < q; c += HP_SWEEP_THREADS)
-            if (c < lc0 || c >= lc1) v_leaf[c] = xget(slot + ls + c, abort_flag);
+            v_leaf[c] = (c >= lc0 && c < lc1) ? v_own[c - lc0] : xget(slot + ls + c, abort_flag);
         if (nrows > 0) {
             for (int e = tid; e < NS; e += HP_SWEEP_THREADS) {
                 int j = rho_j, kap = rho_kap;
@@ -335,19 +318,34 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
                 rho[e] = csub(vs, cadd(va, vc));
             }
         }
-        __syncthreads();                                                          // sync a
-        HP_TICK(1);
-        // separator rows (critical path): one warp per row, warps 1..
-        if (warp > 0) {
-            for (int rr = warp - 1; rr < nrows; rr += nwarps - 1) {
-                cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
-                const cplx* nr = Np + (size_t)rr * NSP;
-                int e = lane;
-                for (; e + 32 < NS; e += 64) { acc = cfma(nr[e], rho[e], acc); acc2 = cfma(nr[e + 32], rho[e + 32], acc2); }
-                if (e < NS) acc = cfma(nr[e], rho[e], acc);
-                acc = hp_warp_sum2(cadd(acc, acc2));
-                if (lane == 0) { xput(slot + a.oXS + row0 + rr, acc); xrow[rr] = acc; }
+        __syncthreads();
+        HP_TICK(3);
+        // separator rows first (they are on the critical path): threads over the columns of N, 4 rows at a time
+        for (int r0 = 0; r0 < nrows; r0 += 4) {
+            cplx acc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = cmake(0.0, 0.0);
+            for (int e = tid; e < NS; e += HP_SWEEP_THREADS) {
+                cplx r = rho[e];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (r0 + i < nrows) acc[i] = cfma(Np[(size_t)(r0 + i) * NSP + e], r, acc[i]);
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = hp_warp_sum2(acc[i]);
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nred[warp * 4 + i] = acc[i];
+            }
+            __syncthreads();
+            if (tid < 4 && r0 + tid < nrows) {
+                cplx t = nred[tid];
+#pragma unroll
+                for (int w = 1; w < HP_SWEEP_THREADS / 32; ++w) t = cadd(t, nred[w * 4 + tid]);
+                xput(slot + a.oXS + row0 + r0 + tid, t);
+                xrow[r0 + tid] = t;
+            }
+            if (r0 + 4 < nrows) __syncthreads();
         }
         // leaf product: lanes over the rows of Wp (odd row stride -> conflict-free), warps over column subsets
         for (int cc = lane; cc < ncols; cc += 32) {
@@ -358,104 +356,80 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
             if (c < q) acc = cfma(wr[c], v_leaf[c], acc);
             y0w[(size_t)warp * CW + cc] = cadd(acc, acc2);
         }
-        __syncthreads();                                                          // sync b
-        HP_TICK(2);
-        // ---- tail (chain warp): S3 of this strip, S1 of the next
-        if (chain) {
+        HP_TICK(4);
+        // ---- S3
+        if (tid < 2 * b) {
+            int side = tid / b, kap = tid - side * b;
+            int j = l - 1 + side;
+            xlr[tid] = (j >= 0 && j < P - 1) ? xget(slot + a.oXS + (size_t)j * b + kap, abort_flag) : cmake(0.0, 0.0);
+        }
+        __syncthreads();
+        HP_TICK(5);
+        // correction: warp w takes the interface components kap = w, w+8, ...; lanes run over the columns
+        for (int cc = lane; cc < ncols; cc += 32) {
+            cplx acc = cmake(0.0, 0.0);
+            for (int kap = warp; kap < 2 * b; kap += nwarps) acc = cfma(Gp[(size_t)kap * CW + cc], xlr[kap], acc);
+            ypart[(size_t)warp * CW + cc] = acc;
+        }
+        __syncthreads();
+        if (tid < ncols) {
+            int c = c0 + tid;
+            cplx y = cmake(0.0, 0.0);
 #pragma unroll
-            for (int i = 0; i < HP_KPL; ++i) {
-                int t = lane + 32 * i;
-                if (t < 2 * b) {
-                    int side = t / b, kap = t - side * b;
-                    int j = l - 1 + side;
-                    xlr[t] = (j >= 0 && j < P - 1) ? xget(slot + a.oXS + (size_t)j * b + kap, abort_flag) : cmake(0.0, 0.0);
+            for (int w = 0; w < HP_SWEEP_THREADS / 32; ++w) y = cadd(y, csub(y0w[(size_t)w * CW + tid], ypart[(size_t)w * CW + tid]));
+            if (a.mode == 2) {
+                a.yout[c] = y;
+            } else if (a.mode == 0) {
+                // u_{m+1} -= c3(row m+1) y ; the result is the input of strip m+1
+                cplx cp = cmul(rfac, cis1);
+                cplx un = cfms(cp, y, upre);
+                a.u[(size_t)m * n + c] = un;
+                v_own[tid] = un;
+            } else {
+                cplx un = a.diag_mode == 0 ? csub(ubase, y) : y;
+                a.u[(size_t)(m - 1) * n + c] = un;
+                if (more) {
+                    // input of strip m-1: u_{m-1} (+/-) c4(row m-1) u_m
+                    cplx cp = cmul(cmul(rfac, cis1), sgn);
+                    ubase = upre;
+                    v_own[tid] = cfma(cp, un, upre);
                 }
             }
-            __syncwarp();
-            HP_TICK(3);
-#pragma unroll
-            for (int i = 0; i < HP_CPL; ++i) {
-                int cc = lane + 32 * i;
-                if (cc < ncols) {
-                    int c = c0 + cc;
-                    cplx y = cmake(0.0, 0.0), y2 = cmake(0.0, 0.0);
-                    for (int w = 0; w < nwarps; w += 2) { y = cadd(y, y0w[(size_t)w * CW + cc]); y2 = cadd(y2, y0w[(size_t)(w + 1) * CW + cc]); }
-                    int kap = 0;
-                    for (; kap + 1 < 2 * b; kap += 2) {
-                        y = cfms(Gp[(size_t)kap * CW + cc], xlr[kap], y);
-                        y2 = cfms(Gp[(size_t)(kap + 1) * CW + cc], xlr[kap + 1], y2);
-                    }
-                    y = cadd(y, y2);
-                    cplx vnext = cmake(0.0, 0.0);
-                    if (a.mode == 2) {
-                        a.yout[c] = y;
-                    } else if (a.mode == 0) {
-                        // u_{m+1} -= c3(row m+1) y ; the result is the input of strip m+1
-                        cplx un = cfms(cmul(rfac, cis1[i]), y, upre[i]);
-                        a.u[(size_t)m * n + c] = un;
-                        vnext = un;
-                    } else {
-                        cplx un = a.diag_mode == 0 ? csub(ubase[i], y) : y;
-                        a.u[(size_t)(m - 1) * n + c] = un;
-                        // input of strip m-1: u_{m-1} (+/-) c4(row m-1) u_m
-                        vnext = cfma(cmul(cmul(rfac, cis1[i]), sgn), un, upre[i]);
-                        ubase[i] = upre[i];
-                    }
-                    if (more) {
-                        v_own[cc] = vnext;
-                        v_leaf[lc0 + cc] = vnext;
-                        if (K > 1) xput(slot_next + c0 + cc, vnext);
-                    }
-                    if (K > 1) xarm(slot_arm + c0 + cc);
-                }
-            }
-            // separator columns: y_s = x_s[b-1]; the input value of the next strip goes to the next slot
-            if (sep_col >= 0) {
-                cplx y = xrow[tid];
-                if (a.mode == 2) a.yout[sep_col] = y;
-                else if (a.mode == 0) {
-                    cplx un = cfms(cmul(rfac, cis1s), y, usep);
-                    a.u[(size_t)m * n + sep_col] = un;
-                    if (more) xput(slot_next + a.oVS + sep_j, un);
-                } else {
-                    cplx un = a.diag_mode == 0 ? csub(usbase, y) : y;
-                    a.u[(size_t)(m - 1) * n + sep_col] = un;
-                    if (more) xput(slot_next + a.oVS + sep_j, cfma(cmul(cmul(rfac, cis1s), sgn), un, usep));
+        }
+        // separator columns: y_s = x_s[b-1]; the input value of the next strip goes to the next slot
+        if (sep_col >= 0) {
+            cplx y = xrow[tid];
+            if (a.mode == 2) a.yout[sep_col] = y;
+            else if (a.mode == 0) {
+                cplx cp = cmul(rfac, cis1s);
+                cplx un = cfms(cp, y, usep);
+                a.u[(size_t)m * n + sep_col] = un;
+                if (more) xput(slot_next + a.oVS + sep_j, un);
+            } else {
+                cplx un = a.diag_mode == 0 ? csub(usbase, y) : y;
+                a.u[(size_t)(m - 1) * n + sep_col] = un;
+                if (more) {
+                    cplx cp = cmul(cmul(rfac, cis1s), sgn);
                     usbase = usep;
-                }
-                xarm(slot_arm + a.oVS + sep_j);
-            }
-            // re-arm the rest of what this CTA wrote for strip it-1
-#pragma unroll
-            for (int i = 0; i < HP_KPL; ++i) {
-                int t = lane + 32 * i;
-                if (t < 2 * b) {
-                    if (K > 1 && k > 0) xarm(slot_arm + a.oGP + (size_t)g * 2 * b + t);
-                    if (k == 0) xarm(slot_arm + a.oGR + (size_t)l * 2 * b + t);
+                    xput(slot_next + a.oVS + sep_j, cfma(cp, un, usep));
                 }
             }
-            if (tid < nrows) xarm(slot_arm + a.oXS + row0 + tid);
-            __syncwarp();
-            HP_TICK(4);
-            // this warp was the last reader of the stage: refill it with the packet two strips ahead
-            if (TMA && lane == 0) {
-                if (it + 2 < nsteps) {
-                    const char* src = (const char*)(pk_base + (size_t)(m + 2 * step - a.m_lo) * strip_stride);
-                    char* dst = (char*)smem_raw + (it & 1) * stage_bytes;
-                    mbar_expect_tx(&mbar[it & 1], pk_bytes);
-                    for (unsigned int o = 0; o < pk_bytes; o += HP_BULK_CHUNK)
-                        bulk_g2s(dst + o, src + o, min(HP_BULK_CHUNK, pk_bytes - o), &mbar[it & 1]);
-                }
-                if (it + 3 < nsteps) {
-                    const char* src = (const char*)(pk_base + (size_t)(m + 3 * step - a.m_lo) * strip_stride);
-                    for (unsigned int o = 0; o < pk_bytes; o += HP_BULK_CHUNK) bulk_prefetch_l2(src + o, min(HP_BULK_CHUNK, pk_bytes - o));
-                }
+        }
+        __syncthreads();
+        HP_TICK(6);
+        if (TMA && tid == 0) {
+            // every thread is done with this stage: refill it with the packet two strips ahead
+            if (it + 2 < nsteps) {
+                const char* src = (const char*)(pk_base + (size_t)(m + 2 * step - a.m_lo) * strip_stride);
+                char* dst = (char*)smem_raw + (it & 1) * stage_bytes;
+                mbar_expect_tx(&mbar[it & 1], pk_bytes);
+                for (unsigned int o = 0; o < pk_bytes; o += HP_BULK_CHUNK)
+                    bulk_g2s(dst + o, src + o, min(HP_BULK_CHUNK, pk_bytes - o), &mbar[it & 1]);
             }
-            if (more) {
-                if (TMA) mbar_wait(&mbar[(it + 1) & 1], ((it + 1) >> 1) & 1);
-                s1_publish(slot_next, packet(it + 1, mn) + a.lay.offG);
+            if (it + 3 < nsteps) {
+                const char* src = (const char*)(pk_base + (size_t)(m + 3 * step - a.m_lo) * strip_stride);
+                for (unsigned int o = 0; o < pk_bytes; o += HP_BULK_CHUNK) bulk_prefetch_l2(src + o, min(HP_BULK_CHUNK, pk_bytes - o));
             }
-            HP_TICK(5);
         }
         if ((it & 63) == 63) {                 // a runaway spin somewhere: every CTA leaves within 64 strips
             if (tid == 0) s_abort = *((volatile unsigned int*)abort_flag);
@@ -491,11 +465,8 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     a.ih2 = 1.0 / (s->pml.h * s->pml.h);
     a.dbg = s->dbg;
     const int nw = HP_SWEEP_THREADS / 32;
-    if (L.CW > 32 * 4 || 2 * s->b > 64 || L.NR > 32) {
-        hp_set_error("sweep: partition outside the kernel's limits (CW=%d <= 128, 2b=%d <= 64, NR=%d <= 32)", L.CW, 2 * s->b, L.NR);
-        return 1;
-    }
-    size_t small = sizeof(cplx) * ((size_t)(1 + nw) * L.CW + L.QP + L.NSP + 2 * s->b + L.NR + 1) + 2 * sizeof(unsigned long long);
+    size_t small = sizeof(cplx) * ((size_t)(1 + 2 * nw) * L.CW + L.QP + L.NSP + 2 * s->b + L.NR + 1 + (size_t)nw * 2 * s->b + nw * 4) +
+                   2 * sizeof(unsigned long long);
     size_t stage = (L.PK * sizeof(cplx) + 127) & ~(size_t)127;
     int max_smem = 0, dev = 0;
     HP_CUDA(cudaGetDevice(&dev));

@@ -26,8 +26,8 @@ for variant in (0, 1):
     out = np.zeros((L["G"], 8), dtype=np.int64)
     s.lib.hp_debug_phases(s.handle, 0, out.ctypes.data)
     nst = n - 1 - b
-    names = ["tma_wait", "S2_gather", "S2_rows+W", "tail_xs_wait", "tail_S3", "tail_S1"]
+    names = ["tma_wait", "S1", "reduce_wait", "S2_poll", "S2_compute", "S3_poll", "S3"]
     print(f"variant {variant}: {ms:.2f} ms, {1e3 * ms / nst:.2f} us/strip; cycles/strip (mean over CTAs | min | max):")
     for i, nm in enumerate(names):
         print(f"   {nm:9s} {out[:, i].mean() / nst:9.0f} {out[:, i].min() / nst:9.0f} {out[:, i].max() / nst:9.0f}")
-    print("   total     ", out[:, :6].sum(1).mean() / nst, "status", s.lib.hp_sweep_status(s.handle))
+    print("   total     ", out[:, :7].sum(1).mean() / nst, "status", s.lib.hp_sweep_status(s.handle))
