@@ -249,6 +249,29 @@ def run_b200(args):
     t_e2e = e0.elapsed_time(e1) / 1e3
     clk = clocks.stop()
 
+    # ---- secondary kernels of the path: matrix-free stencil SpMV and CSR assembly, device time per launch
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record(); torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / 1e3 / reps
+    xs = [torch.randn(N, dtype=torch.complex128, device=f.device) for _ in range(3)]   # 3 x 268 MB > L2
+    ys = torch.empty_like(f)
+    cnt = [0]
+    def spmv():
+        cnt[0] += 1
+        s.matvec(xs[cnt[0] % 3], ys)
+    t_spmv = timed(spmv, 30)
+    spmv_bytes = N * (16 + 16 + 8)                      # x read, y written, kappa read
+    nnz = 5 * N - 4 * n
+    A_ = s.assemble_csr()
+    t_asm = timed(lambda: lib.hp_assemble_csr(s.handle, A_.indptr.data_ptr(), A_.indices.data_ptr(), A_.data.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream), 5)
+    asm_bytes = nnz * (16 + 4) + (N + 1) * 4 + N * 8    # values + column indices + row pointers written, kappa read
+    del A_, xs
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -275,6 +298,10 @@ def run_b200(args):
                         "launches_timed": sw_n.value, "avg_launch_ms": sw_ms.value / max(sw_n.value, 1),
                         "algorithmic_bytes_per_launch": sw_b.value / max(sw_n.value, 1),
                         "share_of_step": (sw_ms.value / 1e3) / t_dev},
+           "spmv": {"kernel": "hp_stencil_matvec_kernel", "ms": 1e3 * t_spmv, "GB/s": spmv_bytes / t_spmv / 1e9,
+                    "frac_of_hbm_peak": spmv_bytes / t_spmv / 1e9 / peak, "bytes_per_point": 40},
+           "assembly": {"kernel": "hp_assemble_csr_kernel", "ms": 1e3 * t_asm, "GB/s": asm_bytes / t_asm / 1e9,
+                        "frac_of_hbm_peak": asm_bytes / t_asm / 1e9 / peak, "nnz": nnz},
            "clocks": clk,
            "setup": {"seconds_wall": t_setup, "strip_factor_ms_device": s.setup_ms, "factor_bytes": s.precond_bytes,
                      "partition": {k: int(L[k]) for k in ("P", "K", "G", "QP", "CW", "NS", "NR", "PK")}},

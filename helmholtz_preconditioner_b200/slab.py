@@ -1,0 +1,189 @@
+"""Slab decomposition of the solve across the GPUs of one box (one process per GPU, torch.distributed).
+
+The grid rows (x2 index, the sweep direction of algo2_4, /root/reference/code.py:356-385) are cut into
+contiguous slabs, rank r owns rows R[r] .. R[r+1]-1 (0-based).  Per rank:
+  * Krylov vectors hold the rank's rows only; dot products are all-reduced              (NCCL / gloo)
+  * the stencil matvec needs one halo row from each neighbour                            (send/recv)
+  * strip T_m (b+1 <= m <= n) lives with its input row m-1, so rank r factors and applies the strips
+    m = R[r]+1 .. R[r+1]; the front block H_F lives on rank 0 (which must own rows 0..b)
+  * the sweeps are a chain over the strips, hence over the ranks: the forward sweep hands the updated first
+    row of the next slab downstream, the backward sweep hands the final first row upstream.  Only one rank
+    sweeps at a time - the decomposition buys memory capacity (the strip factors dominate), not sweep speed.
+
+`backend` is the per-rank compute object: HelmholtzSolver on a GPU, or any object with the same staged
+methods (the CPU tests drive the message schedule with a numpy stand-in over gloo).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def slab_bounds(n, b, world):
+    """R[0..world]: rank r owns rows R[r]..R[r+1]-1.  Rank 0 must own rows 0..b (front block + row b)."""
+    R = [(n * r) // world for r in range(world + 1)]
+    if world > 1 and R[1] < b + 1:
+        raise ValueError(f"slab of rank 0 ({R[1]} rows) must contain the front block and one more row ({b + 1} rows)")
+    return R
+
+
+class SlabSolver:
+    """Distributed operator/preconditioner on slab-distributed vectors (local shape (rows, n), flattened)."""
+
+    def __init__(self, backend, n, b, rank, world, group=None, device="cpu"):
+        self.s, self.n, self.b, self.rank, self.world, self.group = backend, n, b, rank, world, group
+        self.R = slab_bounds(n, b, world)
+        self.j0, self.j1 = self.R[rank], self.R[rank + 1]
+        self.rows = self.j1 - self.j0
+        self.device = device
+        # strips of this rank: m-1 in [j0, j1)  ->  m in [j0+1, j1], clipped to b+1..n
+        self.m_lo, self.m_hi = max(b + 1, self.j0 + 1), min(n, self.j1)
+        # local work buffer with one ghost row below (row j0-1) and above (row j1)
+        self.buf = torch.zeros((self.rows + 2) * n, dtype=torch.complex128, device=device)
+        self.south = torch.zeros(n, dtype=torch.complex128, device=device)
+        self.north = torch.zeros(n, dtype=torch.complex128, device=device)
+
+    # -- communication helpers ------------------------------------------------------------------------
+    def _send(self, t, dst):
+        dist.send(t.contiguous(), dst, group=self.group)
+
+    def _recv(self, t, src):
+        dist.recv(t, src, group=self.group)
+
+    def _row(self, j):
+        """view of global row j inside the ghosted buffer (j0-1 <= j <= j1)."""
+        o = (j - (self.j0 - 1)) * self.n
+        return self.buf[o:o + self.n]
+
+    # -- operator -------------------------------------------------------------------------------------
+    def matvec(self, x, out):
+        """out = A x on the slab; exchanges the boundary rows with the neighbours first."""
+        n, r, w = self.n, self.rank, self.world
+        first, last = x[:n], x[(self.rows - 1) * n:]
+        reqs = []
+        if w > 1:
+            ops = []
+            if r > 0:
+                ops += [dist.P2POp(dist.isend, first.contiguous(), r - 1, self.group), dist.P2POp(dist.irecv, self.south, r - 1, self.group)]
+            if r < w - 1:
+                ops += [dist.P2POp(dist.isend, last.contiguous(), r + 1, self.group), dist.P2POp(dist.irecv, self.north, r + 1, self.group)]
+            reqs = dist.batch_isend_irecv(ops) if ops else []
+            for q in reqs:
+                q.wait()
+        self.s.matvec_rows(self.j0, self.j1, x, self.south if r > 0 else None, self.north if r < w - 1 else None, out)
+        return out
+
+    # -- preconditioner -------------------------------------------------------------------------------
+    def precond_apply(self, x, out, diag="reference"):
+        """out = M x (algo2_4) on slab-distributed vectors."""
+        n, b, r, w = self.n, self.b, self.rank, self.world
+        own = self.buf[n:(self.rows + 1) * n]
+        own.copy_(x)
+        buf, row0 = self.buf, self.j0 - 1                    # the buffer starts at global row j0-1
+        # ghost row above = first row of the next slab (initial values: the forward sweep updates it)
+        if r > 0:
+            self._send(own[:n], r - 1)
+        if r < w - 1:
+            self._recv(self._row(self.j1), r + 1)
+        # forward chain
+        if r == 0:
+            self.s.front_begin_buf(buf, row0)
+        else:
+            self._recv(self._row(self.j0), r - 1)            # first own row, updated by the previous rank
+        m_to = min(self.m_hi, n - 1)
+        if self.m_lo <= m_to:
+            self.s.sweep_forward_buf(buf, row0, self.m_lo, m_to)
+        if r < w - 1:
+            self._send(self._row(self.j1), r + 1)
+        # backward chain
+        if r < w - 1:
+            self._recv(self._row(self.j1), r + 1)            # final first row of the next slab
+        if self.m_lo <= self.m_hi:
+            self.s.sweep_backward_buf(buf, row0, self.m_hi, self.m_lo, diag)
+        if r > 0:
+            self._send(self._row(self.j0), r - 1)
+        else:
+            self.s.front_end_buf(buf, row0)
+        out.copy_(own)
+        return out
+
+
+def distributed_gmres_setup(n, b, omega, const, c_mat, rank, world, group, device, P=0, K=0):
+    """HelmholtzSolver of this rank with its strips factored, wrapped in a SlabSolver."""
+    from .solver import HelmholtzSolver
+    s = HelmholtzSolver(n, b, omega, const, c_mat, device=device)
+    R = slab_bounds(n, b, world)
+    m_lo, m_hi = max(b + 1, R[rank] + 1), min(n, R[rank + 1])
+    s.setup_preconditioner(P, K, m_lo, m_hi)
+    return SlabSolver(s, n, b, rank, world, group, device=device)
+
+
+def bench_distributed(args, w, make_fields, config_dict, ClockSampler):
+    """bench.py for N > 1: weak scaling, one slab per rank, GMRES(20) inner iterations of the global problem."""
+    import json
+    import os
+    import time
+    from . import _lib
+    from .gmres import DeviceVectors, gmres
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    lib = _lib.require_device()
+    omega, c_mat, f_mat = make_fields(w)
+    n, b = w["n"], w["b"]
+    dev = torch.device(f"cuda:{local}")
+    t0 = time.time()
+    S = distributed_gmres_setup(n, b, omega, w["const"], c_mat, rank, world, None, dev)
+    torch.cuda.synchronize()
+    t_setup = time.time() - t0
+    f_loc_host = torch.from_numpy(np.ascontiguousarray(f_mat[S.j0:S.j1].ravel())).pin_memory()
+    f = f_loc_host.to(dev)
+    vec = DeviceVectors(f.numel(), dev, group=dist.group.WORLD)
+    mv = lambda x, out: S.matvec(x, out)                       # noqa: E731
+    ps = lambda x, out: S.precond_apply(x, out)                # noqa: E731
+
+    def iterations(k, rhs):
+        return gmres(mv, ps, rhs, vec=vec, rtol=0.0, atol=0.0, restart=20, maxiter=k, nglobal=n * n)
+
+    iterations(args.warmup, f)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.hp_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); dist.barrier()
+    e0.record()
+    u, info, hist = iterations(args.steps, f)
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    t_dev = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)
+    dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    launches = torch.tensor([lib.hp_launch_count() - l0], device=dev)
+    dist.all_reduce(launches)
+    # end to end: host slab of f -> device, K iterations, slab of u -> host
+    u_host = torch.empty(f.numel(), dtype=torch.complex128).pin_memory()
+    torch.cuda.synchronize(); dist.barrier()
+    e0.record()
+    f2 = f_loc_host.to(dev, non_blocking=True)
+    u2, _, _ = iterations(args.steps, f2)
+    u_host.copy_(u2, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    t_e2e = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)
+    dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    fb = torch.tensor([float(S.s.precond_bytes)], device=dev)
+    dist.all_reduce(fb)
+    if rank == 0:
+        clk = clocks.stop()
+        out = {"metric": "precond. Krylov iters/s at 4096^2 2D", "value": args.steps / t_dev.item(), "unit": "iters/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev.item() / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)",
+               "data": "synthetic", "config": config_dict(w, world),
+               "e2e": {"value": args.steps / t_e2e.item(), "unit": "iters/s",
+                       "h2d_bytes_per_step": n * n * 16 / args.steps, "d2h_bytes_per_step": n * n * 16 / args.steps + 16 * 22},
+               "gpu_launches": int(launches.item()), "clocks": clk,
+               "setup": {"seconds_wall": t_setup, "factor_bytes_all_ranks": fb.item()},
+               "note": ("weak scaling: 4096^2 grid points per GPU, one global problem of n^2 points; the sweeps of the "
+                        "preconditioner are a sequential chain over the strips, so the slabs take turns (DESIGN.md, multi-GPU)"),
+               "residual_last": hist[-1] if hist else None}
+        print(json.dumps(out))
+    dist.destroy_process_group()

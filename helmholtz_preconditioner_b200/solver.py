@@ -163,6 +163,24 @@ class HelmholtzSolver:
                    "hp_precond_apply")
         return out
 
+    # staged calls on a slab buffer whose first row is global row `row0` (slab decomposition, slab.py): the
+    # kernels index the field by absolute row, so they get the address global row 0 would have
+    def _base(self, buf, row0):
+        return buf.data_ptr() - row0 * self.n * 16
+
+    def front_begin_buf(self, buf, row0):
+        _lib.check(self.lib.hp_front_begin(self.handle, self._base(buf, row0), _stream()), "hp_front_begin")
+
+    def front_end_buf(self, buf, row0):
+        _lib.check(self.lib.hp_front_end(self.handle, self._base(buf, row0), _stream()), "hp_front_end")
+
+    def sweep_forward_buf(self, buf, row0, m_from, m_to):
+        _lib.check(self.lib.hp_sweep_forward(self.handle, self._base(buf, row0), m_from, m_to, _stream()), "hp_sweep_forward")
+
+    def sweep_backward_buf(self, buf, row0, m_from, m_to, diag="reference"):
+        _lib.check(self.lib.hp_sweep_backward(self.handle, self._base(buf, row0), m_from, m_to, DIAG_MODES[diag], _stream()),
+                   "hp_sweep_backward")
+
     # staged calls (slab decomposition)
     def front_begin(self, u):
         _lib.check(self.lib.hp_front_begin(self.handle, _ptr(u), _stream()), "hp_front_begin")

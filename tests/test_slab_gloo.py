@@ -1,0 +1,118 @@
+"""Host logic of the slab decomposition (helmholtz_preconditioner_b200/slab.py) with world_size 2 and 3 over gloo on
+the CPU: the message schedule, halo exchange and strip ownership are driven with a numpy stand-in for the
+per-rank kernels (built on the oracle), and the distributed result must equal the single-process oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import helmholtz_oracle as orc
+
+
+class NumpyBackend:
+    """The staged per-rank operations of HelmholtzSolver, on CPU tensors, from the oracle's pieces."""
+
+    def __init__(self, n, b, omega, const, c_mat):
+        h = 1 / (n + 1)
+        self.n, self.b = n, b
+        self.p = dict(b=b, const=const, eta=b * h, omega=omega, h=h, n=n, c_mat=c_mat)
+        self.P = orc.SweepingPreconditioner(**self.p)
+        self.c = orc.stencil_coeffs(np.arange(1, n + 1), None, **self.p)
+
+    def _rows(self, buf, row0):
+        return buf.numpy().reshape(-1, self.n), row0
+
+    def front_begin_buf(self, buf, row0):
+        u, r0 = self._rows(buf, row0)
+        b, n = self.b, self.n
+        self.TF = self.P.lu_HF.solve(u[0 - r0:b - r0].ravel())
+        u[b - r0] -= self.P.lo[b] * self.TF[-n:]
+
+    def front_end_buf(self, buf, row0):
+        u, r0 = self._rows(buf, row0)
+        b, n = self.b, self.n
+        Au = np.zeros(b * n, complex)
+        Au[-n:] = self.P.up[b - 1] * u[b - r0]
+        u[0 - r0:b - r0] = (self.TF - self.P.lu_HF.solve(Au)).reshape(b, n)
+
+    def sweep_forward_buf(self, buf, row0, m_from, m_to):
+        u, r0 = self._rows(buf, row0)
+        for m in range(m_from, m_to + 1):
+            u[m - r0] -= self.P.lo[m] * self.P.T(m, u[m - 1 - r0])
+
+    def sweep_backward_buf(self, buf, row0, m_from, m_to, diag):
+        u, r0 = self._rows(buf, row0)
+        n = self.n
+        for m in range(m_from, m_to - 1, -1):
+            v = u[m - 1 - r0].copy()
+            if m < n:
+                v += self.P.up[m - 1] * u[m - r0]
+            u[m - 1 - r0] = u[m - 1 - r0] - self.P.T(m, v)
+
+    def matvec_rows(self, j_lo, j_hi, x, south, north, out):
+        n = self.n
+        c1, c2, c3, c4, c5 = (c[j_lo:j_hi] for c in self.c)
+        u = x.numpy().reshape(-1, n)
+        y = c5 * u
+        y[:, 1:] += c1[:, 1:] * u[:, :-1]
+        y[:, :-1] += c2[:, :-1] * u[:, 1:]
+        y[1:] += c3[1:] * u[:-1]
+        y[:-1] += c4[:-1] * u[1:]
+        if south is not None:
+            y[0] += c3[0] * south.numpy()
+        if north is not None:
+            y[-1] += c4[-1] * north.numpy()
+        out.copy_(torch.from_numpy(y.ravel()))
+
+
+def _worker(rank, world, port, n, b, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from helmholtz_preconditioner_b200.slab import SlabSolver
+    omega = 2 * np.pi * 4 + 2j
+    c_mat, f_mat = orc.init_c1_f1(omega, n)
+    be = NumpyBackend(n, b, omega, 61.0, c_mat)
+    S = SlabSolver(be, n, b, rank, world)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    xl = torch.from_numpy(x[S.j0:S.j1].ravel().copy())
+    out = torch.empty_like(xl)
+    S.precond_apply(xl, out)
+    ref = be.P.apply(x.ravel()).reshape(n, n)[S.j0:S.j1].ravel()
+    e1 = np.linalg.norm(out.numpy() - ref) / np.linalg.norm(ref)
+    S.matvec(xl, out)
+    ref2 = orc.stencil_matvec(x.ravel(), **be.p).reshape(n, n)[S.j0:S.j1].ravel()
+    e2 = np.linalg.norm(out.numpy() - ref2) / np.linalg.norm(ref2)
+    ret[rank] = (e1, e2, S.m_lo, S.m_hi)
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_schedule_matches_oracle(world):
+    n, b = 40, 5
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n, b, ret), nprocs=world, join=True)
+    strips = []
+    for r in range(world):
+        e1, e2, m_lo, m_hi = ret[r]
+        assert e1 < 1e-12 and e2 < 1e-13, (r, e1, e2)
+        strips += list(range(m_lo, m_hi + 1))
+    assert strips == list(range(b + 1, n + 1))      # every strip has exactly one owner
+
+
+def test_slab_bounds():
+    from helmholtz_preconditioner_b200.slab import slab_bounds
+    assert slab_bounds(4096, 12, 8) == [512 * r for r in range(9)]
+    with pytest.raises(ValueError):
+        slab_bounds(40, 12, 8)
