@@ -42,6 +42,9 @@ __global__ void hp_front_factor_kernel(int n, int b, double ih2, cplx omega2, co
 
 // mode 0: out[j][.] = Tri_j^{-1} in[j][.] for the rows j = row0 .. row0 + nrows - 1  (thread per row)
 // mode 1: single row j = b-1 with rhs = upc * u_next,  out[.] = base[.] - solution      (code.py:381-384)
+// The recurrences are sequential in i; their operands are not, so they are fetched HP_FRONT_U steps ahead
+// into registers (and a few hundred steps ahead into L2) and only the complex multiply-add chain is exposed.
+#define HP_FRONT_U 16
 __global__ void hp_front_solve_kernel(int n, int b, int row0, int nrows, int mode, const cplx* __restrict__ low,
                                       const cplx* __restrict__ invd, const cplx* __restrict__ up,
                                       const cplx* in, cplx* out, const cplx* base, cplx upfac,
@@ -52,20 +55,55 @@ __global__ void hp_front_solve_kernel(int n, int b, int row0, int nrows, int mod
     const cplx* r = in + (size_t)t * n;
     cplx* y = work + (size_t)t * n;
     cplx prev = cmake(0.0, 0.0);
-#pragma unroll 4
-    for (int i = 0; i < n; ++i) {
-        cplx rhs = r[i];
-        if (mode == 1) rhs = cmul(cmul(upfac, is1t[2 * (i + 1)]), rhs);
-        prev = cfms(low[(size_t)i * b + j0], prev, rhs);
-        y[i] = prev;
+    for (int i0 = 0; i0 < n; i0 += HP_FRONT_U) {
+        cplx rr[HP_FRONT_U], ll[HP_FRONT_U];
+        if (i0 + 256 < n) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(r + i0 + 256));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(low + (size_t)(i0 + 256) * b + j0));
+        }
+#pragma unroll
+        for (int k = 0; k < HP_FRONT_U; ++k) {
+            int i = i0 + k;
+            if (i < n) {
+                rr[k] = r[i];
+                ll[k] = low[(size_t)i * b + j0];
+                if (mode == 1) rr[k] = cmul(cmul(upfac, is1t[2 * (i + 1)]), rr[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < HP_FRONT_U; ++k) {
+            int i = i0 + k;
+            if (i < n) { prev = cfms(ll[k], prev, rr[k]); rr[k] = prev; }
+        }
+#pragma unroll
+        for (int k = 0; k < HP_FRONT_U; ++k)
+            if (i0 + k < n) y[i0 + k] = rr[k];
     }
     cplx xn = cmake(0.0, 0.0);
     cplx* o = out + (size_t)t * n;
-#pragma unroll 4
-    for (int i = n - 1; i >= 0; --i) {
-        size_t f = (size_t)i * b + j0;
-        xn = cmul(cfms(up[f], xn, y[i]), invd[f]);
-        o[i] = mode == 1 ? csub(base[i], xn) : xn;
+    for (int i1 = n - 1; i1 >= 0; i1 -= HP_FRONT_U) {
+        cplx yy[HP_FRONT_U], uu[HP_FRONT_U], dd[HP_FRONT_U], bb[HP_FRONT_U];
+        if (i1 - 256 >= 0) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(up + (size_t)(i1 - 256) * b + j0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(invd + (size_t)(i1 - 256) * b + j0));
+        }
+#pragma unroll
+        for (int k = 0; k < HP_FRONT_U; ++k) {
+            int i = i1 - k;
+            if (i >= 0) {
+                size_t f = (size_t)i * b + j0;
+                yy[k] = y[i]; uu[k] = up[f]; dd[k] = invd[f];
+                if (mode == 1) bb[k] = base[i];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < HP_FRONT_U; ++k) {
+            int i = i1 - k;
+            if (i >= 0) { xn = cmul(cfms(uu[k], xn, yy[k]), dd[k]); yy[k] = mode == 1 ? csub(bb[k], xn) : xn; }
+        }
+#pragma unroll
+        for (int k = 0; k < HP_FRONT_U; ++k)
+            if (i1 - k >= 0) o[i1 - k] = yy[k];
     }
 }
 
