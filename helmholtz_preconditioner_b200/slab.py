@@ -13,9 +13,13 @@ contiguous slabs, rank r owns rows R[r] .. R[r+1]-1 (0-based).  Per rank:
 `backend` is the per-rank compute object: HelmholtzSolver on a GPU, or any object with the same staged
 methods (the CPU tests drive the message schedule with a numpy stand-in over gloo).
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
 
 
 def slab_bounds(n, b, world):
