@@ -57,6 +57,7 @@ struct hp_solver {
     std::vector<int> leaf_start_h, leaf_q_h, sep_h;
     int *leaf_start = nullptr, *leaf_q = nullptr, *sep = nullptr;   // device copies
     cplx* packets = nullptr;
+    cplx* mleaf = nullptr;        // transfer matrices of the pipelined sweep: [strip][dir][leaf][2b][2b]
     int64_t bytes = 0;
     double setup_ms = 0.0;
     // front block: Thomas factors of the b tridiagonal diagonal blocks (reference H_F)

@@ -122,6 +122,44 @@ __global__ void __launch_bounds__(128) hp_sep_rows_kernel(HpSetupArgs a) {
     hp_sep_row(nrow, a.Njj + o, a.PF + o, a.PB + o, ns, j, kap, b);
 }
 
+// Transfer matrices of the pipelined sweep kernel (csrc/hp_sweep.cu).  The interface data of strip m is linear
+// in the separator solution x of the previous strip of the sweep:  g_l(m) = gb_l(m) + M_l(m) [x_left; x_right],
+//   M_l(m)[kap'][kap] = sum_c Gc(m)[kap'][c] coef[c] Gc(mprev)[kap][c],   Gc = [Gf; Gl] of leaf l,
+//   forward  (dir 0): mprev = m-1, coef[c] = A_{m,m-1}[c]   (couples grid rows m-1, m)
+//   backward (dir 1): mprev = m+1, coef[c] = A_{m,m+1}[c]   (couples grid rows m, m+1)
+// stored transposed, mleaf[((m-m_lo)*2 + dir)*P + l][kap][kap'], so that lanes over kap' read contiguously.
+// CTA -> (strip, dir, leaf); both G blocks are staged in shared memory.
+__global__ void __launch_bounds__(256) hp_mleaf_kernel(const cplx* __restrict__ packets, HpLayout lay,
+        const int* __restrict__ leaf_start, const int* __restrict__ leaf_q, int m_lo, int m_hi, int b, double ih2,
+        const cplx* __restrict__ s2t, const cplx* __restrict__ is1t, cplx* __restrict__ mleaf) {
+    extern __shared__ double2 sm[];
+    const int l = blockIdx.x % lay.P, dir = (blockIdx.x / lay.P) & 1, mi = blockIdx.x / (2 * lay.P);
+    const int m = m_lo + mi, mprev = dir == 0 ? m - 1 : m + 1;
+    if (mprev < m_lo || mprev > m_hi) return;                     // stays zero (never used: first strip of a sweep)
+    const int q = leaf_q[l], K = lay.K, b2 = 2 * b, ls = leaf_start[l];
+    cplx* Ga = sm;                       // [2b][q]  Gc(m)
+    cplx* Gb = sm + (size_t)b2 * lay.QP; // [2b][q]  coef * Gc(mprev)
+    const cplx rf = cscale(ih2, s2t[2 * (dir == 0 ? m - 1 : m) + 1]);
+    for (int e = threadIdx.x; e < b2 * q; e += blockDim.x) {
+        int kap = e / q, c = e - kap * q;
+        int k = ((c + 1) * K - 1) / q, lc0 = (q * k) / K;
+        size_t off = (size_t)(l * K + k) * lay.PK + lay.offG + (size_t)kap * lay.CW + (c - lc0);
+        Ga[kap * lay.QP + c] = packets[(size_t)(m - m_lo) * lay.G * lay.PK + off];
+        cplx coef = cmul(rf, is1t[2 * (ls + c + 1)]);
+        Gb[kap * lay.QP + c] = cmul(coef, packets[(size_t)(mprev - m_lo) * lay.G * lay.PK + off]);
+    }
+    __syncthreads();
+    cplx* out = mleaf + ((size_t)(mi * 2 + dir) * lay.P + l) * b2 * b2;
+    for (int e = threadIdx.x; e < b2 * b2; e += blockDim.x) {
+        int kap = e / b2, kapp = e - kap * b2;                    // out[kap][kap']
+        cplx acc = cmake(0.0, 0.0);
+        const cplx* ga = Ga + kapp * lay.QP;
+        const cplx* gb = Gb + kap * lay.QP;
+        for (int c = 0; c < q; ++c) acc = cfma(ga[c], gb[c], acc);
+        out[e] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // partition
 // ------------------------------------------------------------------------------------------------------
@@ -172,6 +210,7 @@ static int hp_choose_layout(hp_solver* s, int nstrips, int P_req, int K_req, HpL
 
 void hp_free_strips(hp_solver* s) {
     cudaFree(s->packets); s->packets = nullptr;
+    cudaFree(s->mleaf); s->mleaf = nullptr;
     cudaFree(s->leaf_start); s->leaf_start = nullptr;
     cudaFree(s->leaf_q); s->leaf_q = nullptr;
     cudaFree(s->sep); s->sep = nullptr;
@@ -260,6 +299,17 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
             hp_count_launch(); hp_sep_rows_kernel<<<(t7 + 127) / 128, 128, 0, st>>>(a);
         }
         HP_CUDA(cudaGetLastError());
+    }
+    {   // transfer matrices of the pipelined sweep
+        size_t mbytes = (size_t)nstrips * 2 * P * 4 * bb * sizeof(cplx);
+        HP_CUDA(cudaMalloc(&s->mleaf, mbytes));
+        HP_CUDA(cudaMemsetAsync(s->mleaf, 0, mbytes, st));
+        size_t smem = sizeof(cplx) * 2 * 2 * b * L.QP;
+        HP_CUDA(cudaFuncSetAttribute(hp_mleaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hp_count_launch(); hp_mleaf_kernel<<<nstrips * 2 * P, 256, smem, st>>>(s->packets, L, s->leaf_start, s->leaf_q, m_lo, m_hi, b,
+                                                                            1.0 / (s->pml.h * s->pml.h), s->s2t, s->is1t, s->mleaf);
+        HP_CUDA(cudaGetLastError());
+        s->bytes += (int64_t)mbytes;
     }
     cudaEventRecord(e1, st);
     HP_CUDA(cudaStreamSynchronize(st));

@@ -23,103 +23,11 @@
 // double-buffers whole packets in shared memory with cp.async.bulk + mbarrier (issued one strip ahead, with an
 // L2 prefetch two strips ahead); the direct variant (packets too large for two shared-memory stages) reads
 // them from global memory behind an L2 prefetch.
-#include "hp_internal.cuh"
+#include "hp_sweep_common.cuh"
 
 #ifndef HP_SWEEP_THREADS
 #define HP_SWEEP_THREADS 256
 #endif
-#define HP_RING 4
-#define HP_SPIN_LIMIT (1u << 21)
-
-struct HpSweepArgs {
-    int n, b;
-    HpLayout lay;
-    const int *leaf_start, *leaf_q, *sep;
-    const cplx* packets;
-    int m_lo;
-    int mode, m_from, m_to, diag_mode;
-    cplx* u;
-    const cplx* vin;
-    cplx* yout;
-    cplx* xch;                // exchange ring: HP_RING slots of slot_stride complex numbers
-    size_t oGP, oGR, oXS, oVS, slot_stride;
-    unsigned int* bar;        // [1] abort flag (a spin ran into HP_SPIN_LIMIT)
-    const cplx *s2t, *is1t;
-    double ih2;
-    long long* dbg;           // optional [G][8] per-phase cycle sums (thread 0 of every CTA), NULL = off
-};
-
-__device__ __forceinline__ cplx ldcg(const cplx* p) {
-    double2 v = __ldcg(reinterpret_cast<const double2*>(p));
-    return v;
-}
-
-// ---- self-validating exchange words -----------------------------------------------------------------
-#define HP_SENTINEL 0xFFFFFFFFFFFFFFFFull
-__device__ __forceinline__ void xput(cplx* p, cplx v) {
-    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-}
-__device__ __forceinline__ void xarm(cplx* p) {
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %1};" ::"l"(p), "l"(HP_SENTINEL) : "memory");
-}
-__device__ __forceinline__ bool xtry(const cplx* p, cplx& v) {
-    unsigned long long lo, hi;
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
-    v.x = __longlong_as_double((long long)lo);
-    v.y = __longlong_as_double((long long)hi);
-    return lo != HP_SENTINEL && hi != HP_SENTINEL;
-}
-// spin until the word is valid; on a runaway spin raise the abort flag (the kernel then terminates)
-__device__ __forceinline__ cplx xget(const cplx* p, unsigned int* abort_flag) {
-    cplx v;
-    unsigned int spins = 0;
-    while (!xtry(p, v)) {
-        if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); break; }
-        if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) break;
-    }
-    return v;
-}
-
-__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned int bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-__device__ __forceinline__ cplx hp_warp_sum2(cplx v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
-        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
-    }
-    return v;
-}
-// coupling A_{j+1,j}[c] = c3 of grid row j+1 = s2((j+.5)h)/(h^2 s1(ih)) = A_{j,j+1}[c] (c4 of row j); rowfac is
-// the x2 part for the pair (j, j+1), 1-based j
-__device__ __forceinline__ cplx hp_rowfac(const HpSweepArgs& a, int j) { return cscale(a.ih2, a.s2t[2 * j + 1]); }
-
-#define HP_BULK_CHUNK 32768u
 
 template <bool TMA>
 __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs a) {
@@ -441,6 +349,10 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
         for (int i = 0; i < 8; ++i) a.dbg[(size_t)g * 8 + i] = tacc[i];
 }
 
+#define HP2_OFF_COLS 256
+size_t hp_sweep2_smem(const HpLayout& L, int b);
+int hp_sweep2_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st);
+
 int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout, int m_from, int m_to,
                     int diag_mode, cudaStream_t st) {
     if (!s->packets) { hp_set_error("sweep: preconditioner not set up"); return 1; }
@@ -455,7 +367,7 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     HpSweepArgs a;
     a.n = s->n; a.b = s->b; a.lay = s->lay;
     a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
-    a.packets = s->packets; a.m_lo = s->m_lo;
+    a.packets = s->packets; a.mleaf = s->mleaf; a.m_lo = s->m_lo;
     a.mode = mode; a.m_from = m_from; a.m_to = m_to; a.diag_mode = diag_mode;
     a.u = u; a.vin = vin; a.yout = yout;
     a.xch = s->xch; a.bar = s->bar;
@@ -471,17 +383,28 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     int max_smem = 0, dev = 0;
     HP_CUDA(cudaGetDevice(&dev));
     HP_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    bool tma = s->sweep_variant != 1 && 2 * stage + small + 1024 <= (size_t)max_smem;
-    size_t smem = small + (tma ? 2 * stage : 0);
-    if (smem + 1024 > (size_t)max_smem) { hp_set_error("sweep: %zu bytes of shared memory needed, %d available", smem, max_smem); return 1; }
-    const void* fn = tma ? (const void*)hp_sweep_kernel<true> : (const void*)hp_sweep_kernel<false>;
-    if (smem > 48 * 1024) HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // variants: 0 automatic; 1 direct (global loads); 2 staged, block-synchronous phases; 3 pipelined (csrc/hp_sweep2.cu)
+    bool pipe_ok = L.CW <= HP2_OFF_COLS && 2 * s->b <= 64 && L.NR <= 128 && s->mleaf && hp_sweep2_smem(L, s->b) + 1024 <= (size_t)max_smem;
+    bool tma_ok = 2 * stage + small + 1024 <= (size_t)max_smem;
+    int variant = s->sweep_variant;
+    if (variant == 0) variant = pipe_ok ? 3 : (tma_ok ? 2 : 1);
+    if (variant == 3 && !pipe_ok) variant = tma_ok ? 2 : 1;
+    if (variant == 2 && !tma_ok) variant = 1;
     // the exchange ring starts all-sentinel (0xFF bytes); bar[1] = abort flag
     HP_CUDA(cudaMemsetAsync(s->xch, 0xFF, sizeof(cplx) * HP_RING * a.slot_stride, st));
-    void* args[] = {&a};
     hp_count_launch();
     hp_profile_begin(s, st);
-    HP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.G), dim3(HP_SWEEP_THREADS), args, smem, st));
+    if (variant == 3) {
+        if (hp_sweep2_launch(s, a, st)) return 2;
+    } else {
+        bool tma = variant == 2;
+        size_t smem = small + (tma ? 2 * stage : 0);
+        if (smem + 1024 > (size_t)max_smem) { hp_set_error("sweep: %zu bytes of shared memory needed, %d available", smem, max_smem); return 1; }
+        const void* fn = tma ? (const void*)hp_sweep_kernel<true> : (const void*)hp_sweep_kernel<false>;
+        if (smem > 48 * 1024) HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void* args[] = {&a};
+        HP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.G), dim3(HP_SWEEP_THREADS), args, smem, st));
+    }
     hp_profile_end(s, st, (int64_t)(hi - lo + 1) * ((int64_t)L.G * L.PK + 3 * (int64_t)s->n) * (int64_t)sizeof(cplx));
     return 0;
 }

@@ -46,7 +46,7 @@ def test_strips_4096_vs_oracle(hp):
             t = np.zeros(b * n, complex)
             t[-n:] = v.cpu().numpy()
             ref = lu.solve(t)[-n:]
-            for variant in (0, 1):
+            for variant in (1, 2, 3):
                 s.set_sweep_variant(variant)
                 assert rel(s.strip_apply(m, v), ref) < 1e-11
     assert s.sweep_status() == 0
@@ -76,9 +76,13 @@ def test_strip_operator_properties_1024(solver1024):
         # linearity
         y3 = s.strip_apply(m, (2 - 1j) * v1 + v2)
         assert rel(y3, (2 - 1j) * y1 + y2) < 1e-12
-        # the two sweep kernels (TMA-staged and direct) run the same arithmetic
+        # the block-synchronous kernels (direct, TMA-staged) run the same arithmetic; the pipelined one regroups it
         s.set_sweep_variant(1)
-        assert torch.equal(s.strip_apply(m, v1), y1)
+        yd = s.strip_apply(m, v1)
+        s.set_sweep_variant(2)
+        assert torch.equal(s.strip_apply(m, v1), yd)
+        s.set_sweep_variant(3)
+        assert rel(s.strip_apply(m, v1), yd) < 1e-13
         s.set_sweep_variant(0)
     assert s.sweep_status() == 0
 
@@ -89,10 +93,15 @@ def test_preconditioner_properties_1024(solver1024):
     x, y = rnd(N, 3), rnd(N, 4)
     Mx, My = s.precond_apply(x), s.precond_apply(y)
     assert rel(s.precond_apply((0.5 + 2j) * x - y), (0.5 + 2j) * Mx - My) < 1e-11
-    # idempotent call: same input, same bits
+    # idempotent call: same input, same bits; the three kernel variants agree
     assert torch.equal(s.precond_apply(x), Mx)
     s.set_sweep_variant(1)
-    assert torch.equal(s.precond_apply(x), Mx)
+    Md = s.precond_apply(x)
+    s.set_sweep_variant(2)
+    assert torch.equal(s.precond_apply(x), Md)
+    s.set_sweep_variant(3)
+    assert rel(s.precond_apply(x), Md) < 1e-12
+    assert rel(Mx, Md) < 1e-12
     s.set_sweep_variant(0)
     for d in ("reference", "paper"):
         assert torch.isfinite(torch.view_as_real(s.precond_apply(x, diag=d))).all()

@@ -15,7 +15,7 @@ s.setup_preconditioner(P=P, K=K)
 L = s.layout()
 print({k: int(L[k]) for k in ("P", "K", "G", "QP", "CW", "NS", "NR", "PK")}, "setup ms", s.setup_ms)
 u = torch.from_numpy(f_mat.ravel().astype(np.complex128)).cuda()
-for variant in (0, 1):
+for variant in (3, 2):
     s.set_sweep_variant(variant)
     s.sweep_forward(u, b + 1, n - 1)
     torch.cuda.synchronize()
