@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
         // critical group
         // =====================================================================================================
         const int ctid = tid, cw = ctid >> 5;
+        long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
+#define HP_TICK(i) do { if (a.dbg && lane == 0 && (tid == 0 || tid == HP2_CRIT)) { long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
         if (ctid == 0) {
             for (int sidx = 0; sidx < 2 && sidx < nsteps; ++sidx) {
                 int ms = m0 + sidx * step;
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 if (a.mode == 0) usep = ldcg(a.u + (size_t)m * n + sep_col);
                 else if (a.mode == 1 && more) usep = ldcg(a.u + (size_t)(mn - 1) * n + sep_col);
             }
+            if (a.dbg && tid == 0) tprev = clock64();
             // ---- C1: the leaf's first CTA turns the partial gb into GR(t) = sum gb + M(t) x(t-1)
             if (reducer && cw == 0) {
                 if (it > 0) {
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                     __syncwarp();
                     mbar_wait(&mbar[4 + (it & 1)], (it >> 1) & 1);
                 }
+                HP_TICK(0);
                 const cplx* M = reinterpret_cast<const cplx*>(ringM + (it & 1) * m_st);
 #pragma unroll
                 for (int i = 0; i < HP2_KPL; ++i) {
@@ -179,6 +183,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                     }
                 }
                 __syncwarp();
+                HP_TICK(1);
                 if (lane == 0 && it + 2 < nsteps)
                     ring_fill(ringM + (it & 1) * m_st, m_base + (size_t)(m + 2 * step - a.m_lo) * m_stride, m_bytes, &mbar[4 + (it & 1)]);
             }
@@ -203,8 +208,10 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                     }
                     rho[e] = csub(vs, cadd(va, vc));
                 }
+                HP_TICK(2);
                 bar_crit();
                 mbar_wait(&mbar[2 + (it & 1)], (it >> 1) & 1);
+                HP_TICK(3);
                 const cplx* Np = reinterpret_cast<const cplx*>(ringN + (it & 1) * n_st);
                 for (int o = 0; cw + 4 * o < nrows; ++o) {
                     const int rr = cw + 4 * o;
@@ -234,16 +241,20 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                     }
                 }
                 bar_crit();
+                HP_TICK(4);
                 if (ctid == 0 && it + 2 < nsteps)
                     ring_fill(ringN + (it & 1) * n_st, pk_base + (size_t)(m + 2 * step - a.m_lo) * strip_stride + a.lay.offN, n_bytes,
                               &mbar[2 + (it & 1)]);
             }
         }
+        if (a.dbg && tid == 0)
+            for (int i = 0; i < 8; ++i) a.dbg[(size_t)g * 16 + i] = tacc[i];
     } else {
         // =====================================================================================================
         // off-path group
         // =====================================================================================================
         const int ot = tid - HP2_CRIT, ow = ot >> 5;
+        long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
         if (ot == 0) {
             for (int sidx = 0; sidx < 2 && sidx < nsteps; ++sidx)
                 ring_fill(ringWG + sidx * wg_st, pk_base + (size_t)(m0 + sidx * step - a.m_lo) * strip_stride, wg_bytes, &mbar[sidx]);
@@ -287,9 +298,11 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 if (a.mode == 0) unx = ldcg(a.u + (size_t)m * n + c);
                 else if (a.mode == 1 && more) unx = ldcg(a.u + (size_t)(mn - 1) * n + c);
             }
+            if (a.dbg && ot == 0) tprev = clock64();
             // ---- a: gb(t) = Gc(t) vb(t)
             if (live) {
                 mbar_wait(&mbar[it & 1], (it >> 1) & 1);
+                HP_TICK(0);
                 for (int kap = lane; kap < b2; kap += 32) {
                     cplx acc = cmake(0.0, 0.0);
                     const cplx* gr = Gp + (size_t)kap * CW;
@@ -305,6 +318,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                     xarm(slot_arm + a.oGP + (size_t)g * b2 + ot);
                 }
             }
+            HP_TICK(1);
             // ---- b: x(t-1) arrives: finish strip t-1 on the own columns, input of strip t
             cplx v = vbr;
             if (it > 0) {
@@ -313,6 +327,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                     xlr_o[ot] = (j >= 0 && j < P - 1) ? xwait(slot_prev + a.oXS + (size_t)j * b + kap, abort_flag, dead) : cmake(0.0, 0.0);
                 }
                 bar_off();
+                HP_TICK(2);
                 if (col) {
                     cplx corr = cmake(0.0, 0.0), corr2 = cmake(0.0, 0.0);
                     int kap = 0;
@@ -331,6 +346,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 }
             }
             if (!live) break;
+            HP_TICK(3);
             if (col) {
                 v_leaf[lc0 + ot] = v;
                 if (K > 1) { xput(slot + c0 + ot, v); xarm(slot_arm + c0 + ot); }
@@ -339,6 +355,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
             for (int cc = ot; cc < q; cc += HP2_OFF)
                 if (cc < lc0 || cc >= lc1) v_leaf[cc] = xwait(slot + ls + cc, abort_flag, dead);
             bar_off();
+            HP_TICK(4);
             // keep Gc(t) for the correction of the next strip (every read of the old copy is behind the barrier)
             for (int e = ot; e < b2 * CW; e += HP2_OFF) Gprev[e] = Gp[e];
             for (int cc = lane; cc < ncols; cc += 32) {
@@ -350,6 +367,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 y0w[(size_t)ow * CW + cc] = cadd(acc, acc2);
             }
             bar_off();                                   // every thread of the group is done with the stage
+            HP_TICK(5);
             if (ot == 0) {
                 if (it + 2 < nsteps) ring_fill(ringWG + (it & 1) * wg_st, pk_base + (size_t)(m + 2 * step - a.m_lo) * strip_stride, wg_bytes, &mbar[it & 1]);
                 if (it + 3 < nsteps) {
@@ -375,7 +393,10 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 vb[ot] = vbr;
             }
             bar_off();                                   // vb, y0w free for the next strip
+            HP_TICK(6);
         }
+        if (a.dbg && ot == 0)
+            for (int i = 0; i < 8; ++i) a.dbg[(size_t)g * 16 + 8 + i] = tacc[i];
     }
 }
 

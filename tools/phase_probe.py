@@ -23,11 +23,15 @@ for variant in (3, 2):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); s.sweep_forward(u, b + 1, n - 1); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    out = np.zeros((L["G"], 8), dtype=np.int64)
+    out = np.zeros((L["G"], 16), dtype=np.int64)
     s.lib.hp_debug_phases(s.handle, 0, out.ctypes.data)
     nst = n - 1 - b
-    names = ["tma_wait", "S1", "reduce_wait", "S2_poll", "S2_compute", "S3_poll", "S3"]
+    names = (["C1 wait xs", "C1 gpb+M", "C2 wait GR", "C2 bar+N", "C2 rows", "-", "-", "-", "a tma", "a gb", "b wait xs", "b corr", "c gather", "c W", "c tail", "-"]
+             if variant == 3 else ["tma_wait", "S1", "reduce_wait", "S2_poll", "S2_compute", "S3_poll", "S3"])
     print(f"variant {variant}: {ms:.2f} ms, {1e3 * ms / nst:.2f} us/strip; cycles/strip (mean over CTAs | min | max):")
     for i, nm in enumerate(names):
         print(f"   {nm:9s} {out[:, i].mean() / nst:9.0f} {out[:, i].min() / nst:9.0f} {out[:, i].max() / nst:9.0f}")
-    print("   total     ", out[:, :7].sum(1).mean() / nst, "status", s.lib.hp_sweep_status(s.handle))
+    red = np.arange(L["G"]) % L["K"] == 0
+    if variant == 3:
+        print("   reducers only: C1 wait xs %.0f  C1 gpb+M %.0f  C2 wait GR %.0f" % tuple(out[red, i].mean() / nst for i in (0, 1, 2)))
+    print("   total     ", out[:, :8].sum(1).mean() / nst, out[:, 8:].sum(1).mean() / nst, "status", s.lib.hp_sweep_status(s.handle))
