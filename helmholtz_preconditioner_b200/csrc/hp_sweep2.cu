@@ -168,15 +168,20 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 for (int i = 0; i < HP2_KPL; ++i) {
                     int kp = lane + 32 * i;
                     if (kp < b2) {
-                        cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
+                        cplx acc = cmake(0.0, 0.0);
                         for (int kk = 0; kk < K; ++kk) acc = cadd(acc, xwait(slot + a.oGP + (size_t)(g + kk) * b2 + kp, abort_flag, dead));
                         if (it > 0) {
+                            cplx a1 = cmake(0.0, 0.0), a2 = cmake(0.0, 0.0), a3 = cmake(0.0, 0.0);
                             int kap = 0;
-                            for (; kap + 1 < b2; kap += 2) {
+#pragma unroll 2
+                            for (; kap + 3 < b2; kap += 4) {
                                 acc = cfma(M[(size_t)kap * b2 + kp], xlr_c[kap], acc);
-                                acc2 = cfma(M[(size_t)(kap + 1) * b2 + kp], xlr_c[kap + 1], acc2);
+                                a1 = cfma(M[(size_t)(kap + 1) * b2 + kp], xlr_c[kap + 1], a1);
+                                a2 = cfma(M[(size_t)(kap + 2) * b2 + kp], xlr_c[kap + 2], a2);
+                                a3 = cfma(M[(size_t)(kap + 3) * b2 + kp], xlr_c[kap + 3], a3);
                             }
-                            acc = cadd(acc, acc2);
+                            for (; kap < b2; ++kap) acc = cfma(M[(size_t)kap * b2 + kp], xlr_c[kap], acc);
+                            acc = cadd(cadd(acc, a1), cadd(a2, a3));
                         }
                         xput(slot + a.oGR + (size_t)l * b2 + kp, acc);
                         xarm(slot_arm + a.oGR + (size_t)l * b2 + kp);
@@ -189,24 +194,37 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
             }
             // ---- C2: separator right-hand sides and own rows of x_S
             if (nrows > 0) {
-                for (int e = ctid; e < NS; e += HP2_CRIT) {
-                    int j = rho_j0, kap = rho_k0;
-                    if (e != ctid) { j = e / b; kap = e - j * b; }
-                    const cplx* pa = slot + a.oGR + ((size_t)j * 2 + 1) * b + kap;          // Gl of leaf j
-                    const cplx* pc = slot + a.oGR + ((size_t)(j + 1) * 2) * b + kap;        // Gf of leaf j+1
-                    const cplx* pv = slot + a.oVS + j;
-                    const bool need_v = kap == b - 1;
-                    cplx va, vc, vs = cmake(0.0, 0.0);
+                for (int e0 = ctid; e0 < NS; e0 += 4 * HP2_CRIT) {          // up to 4 entries per thread in flight
+                    const cplx *pa[4], *pc[4], *pv[4];
+                    cplx va[4], vc[4], vs[4];
+                    bool need_v[4], have[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        int e = e0 + i * HP2_CRIT;
+                        have[i] = e < NS;
+                        int j = rho_j0, kap = rho_k0;
+                        if (e != ctid && have[i]) { j = e / b; kap = e - j * b; }
+                        pa[i] = slot + a.oGR + ((size_t)j * 2 + 1) * b + kap;          // Gl of leaf j
+                        pc[i] = slot + a.oGR + ((size_t)(j + 1) * 2) * b + kap;        // Gf of leaf j+1
+                        pv[i] = slot + a.oVS + j;
+                        need_v[i] = have[i] && kap == b - 1;
+                        vs[i] = cmake(0.0, 0.0);
+                    }
                     unsigned int spins = 0;
                     for (;;) {
-                        bool ok = xtry(pa, va);
-                        ok = xtry(pc, vc) && ok;
-                        if (need_v) ok = xtry(pv, vs) && ok;
+                        bool ok = true;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (have[i]) { ok = xtry(pa[i], va[i]) && ok; ok = xtry(pc[i], vc[i]) && ok; }
+                            if (need_v[i]) ok = xtry(pv[i], vs[i]) && ok;
+                        }
                         if (ok || *dead) break;
                         if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; break; }
                         if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) { *dead = 1u; break; }
                     }
-                    rho[e] = csub(vs, cadd(va, vc));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (have[i]) rho[e0 + i * HP2_CRIT] = csub(vs[i], cadd(va[i], vc[i]));
                 }
                 HP_TICK(2);
                 bar_crit();
@@ -215,12 +233,17 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 const cplx* Np = reinterpret_cast<const cplx*>(ringN + (it & 1) * n_st);
                 for (int o = 0; cw + 4 * o < nrows; ++o) {
                     const int rr = cw + 4 * o;
-                    cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
+                    cplx acc = cmake(0.0, 0.0), a1 = cmake(0.0, 0.0), a2 = cmake(0.0, 0.0), a3 = cmake(0.0, 0.0);
                     const cplx* nr = Np + (size_t)rr * NSP;
                     int e = lane;
-                    for (; e + 32 < NS; e += 64) { acc = cfma(nr[e], rho[e], acc); acc2 = cfma(nr[e + 32], rho[e + 32], acc2); }
-                    if (e < NS) acc = cfma(nr[e], rho[e], acc);
-                    acc = hp_warp_sum2(cadd(acc, acc2));                               // every lane holds the row sum
+                    for (; e + 96 < NS; e += 128) {
+                        acc = cfma(nr[e], rho[e], acc);
+                        a1 = cfma(nr[e + 32], rho[e + 32], a1);
+                        a2 = cfma(nr[e + 64], rho[e + 64], a2);
+                        a3 = cfma(nr[e + 96], rho[e + 96], a3);
+                    }
+                    for (; e < NS; e += 32) acc = cfma(nr[e], rho[e], acc);
+                    acc = hp_warp_sum2(cadd(cadd(acc, a1), cadd(a2, a3)));           // every lane holds the row sum
                     if (lane == o) {
                         xput(slot + a.oXS + row0 + rr, acc);
                         xarm(slot_arm + a.oXS + row0 + rr);
@@ -292,7 +315,8 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
             const cplx* pk = reinterpret_cast<const cplx*>(ringWG + (it & 1) * wg_st);
             const cplx* Wp = pk;
             const cplx* Gp = pk + a.lay.offG;
-            // early load of the field value vb(t+1) is built from (written by no other thread)
+            // early loads: the row coupling and the field value vb(t+1) is built from (written by no other thread)
+            const cplx rf_it = hp_rowfac(a, a.mode == 1 ? mn : m);
             cplx unx = cmake(0.0, 0.0);
             if (col && live) {
                 if (a.mode == 0) unx = ldcg(a.u + (size_t)m * n + c);
@@ -329,13 +353,17 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 bar_off();
                 HP_TICK(2);
                 if (col) {
-                    cplx corr = cmake(0.0, 0.0), corr2 = cmake(0.0, 0.0);
+                    cplx corr = cmake(0.0, 0.0), c1 = cmake(0.0, 0.0), c2 = cmake(0.0, 0.0), c3 = cmake(0.0, 0.0);
                     int kap = 0;
-                    for (; kap + 1 < b2; kap += 2) {
+#pragma unroll 2
+                    for (; kap + 3 < b2; kap += 4) {
                         corr = cfma(Gprev[(size_t)kap * CW + ot], xlr_o[kap], corr);
-                        corr2 = cfma(Gprev[(size_t)(kap + 1) * CW + ot], xlr_o[kap + 1], corr2);
+                        c1 = cfma(Gprev[(size_t)(kap + 1) * CW + ot], xlr_o[kap + 1], c1);
+                        c2 = cfma(Gprev[(size_t)(kap + 2) * CW + ot], xlr_o[kap + 2], c2);
+                        c3 = cfma(Gprev[(size_t)(kap + 3) * CW + ot], xlr_o[kap + 3], c3);
                     }
-                    corr = cadd(corr, corr2);
+                    for (; kap < b2; ++kap) corr = cfma(Gprev[(size_t)kap * CW + ot], xlr_o[kap], corr);
+                    corr = cadd(cadd(corr, c1), cadd(c2, c3));
                     v = cfma(coefc, corr, vbr);
                     if (a.mode == 2) a.yout[c] = csub(y0prev, corr);
                     else if (a.mode == 0) a.u[(size_t)mp * n + c] = v;                      // row m_{t-1}: final
@@ -359,16 +387,22 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
             // keep Gc(t) for the correction of the next strip (every read of the old copy is behind the barrier)
             for (int e = ot; e < b2 * CW; e += HP2_OFF) Gprev[e] = Gp[e];
             for (int cc = lane; cc < ncols; cc += 32) {
-                cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
+                cplx acc = cmake(0.0, 0.0), a1 = cmake(0.0, 0.0), a2 = cmake(0.0, 0.0), a3 = cmake(0.0, 0.0);
                 const cplx* wr = Wp + (size_t)cc * QP;
                 int cq = ow;
-                for (; cq + 8 < q; cq += 16) { acc = cfma(wr[cq], v_leaf[cq], acc); acc2 = cfma(wr[cq + 8], v_leaf[cq + 8], acc2); }
-                if (cq < q) acc = cfma(wr[cq], v_leaf[cq], acc);
-                y0w[(size_t)ow * CW + cc] = cadd(acc, acc2);
+#pragma unroll 2
+                for (; cq + 24 < q; cq += 32) {
+                    acc = cfma(wr[cq], v_leaf[cq], acc);
+                    a1 = cfma(wr[cq + 8], v_leaf[cq + 8], a1);
+                    a2 = cfma(wr[cq + 16], v_leaf[cq + 16], a2);
+                    a3 = cfma(wr[cq + 24], v_leaf[cq + 24], a3);
+                }
+                for (; cq < q; cq += 8) acc = cfma(wr[cq], v_leaf[cq], acc);
+                y0w[(size_t)ow * CW + cc] = cadd(cadd(acc, a1), cadd(a2, a3));
             }
             bar_off();                                   // every thread of the group is done with the stage
             HP_TICK(5);
-            if (ot == 0) {
+            if (ot == HP2_OFF - 32) {
                 if (it + 2 < nsteps) ring_fill(ringWG + (it & 1) * wg_st, pk_base + (size_t)(m + 2 * step - a.m_lo) * strip_stride, wg_bytes, &mbar[it & 1]);
                 if (it + 3 < nsteps) {
                     const char* src = (const char*)(pk_base + (size_t)(m + 3 * step - a.m_lo) * strip_stride);
@@ -382,10 +416,10 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 for (int w = 1; w < 8; ++w) y0 = cadd(y0, y0w[(size_t)w * CW + ot]);
                 y0prev = y0;
                 if (a.mode == 0) {
-                    coefc = cmul(hp_rowfac(a, m), cis1);                       // A_{m+1,m}
+                    coefc = cmul(rf_it, cis1);                                 // A_{m+1,m}
                     vbr = cfms(coefc, y0, unx);                                // u_{m+1} - coef y0
                 } else if (a.mode == 1) {
-                    coefc = cmul(hp_rowfac(a, mn), cis1);                      // A_{m-1,m}
+                    coefc = cmul(rf_it, cis1);                                 // A_{m-1,m}
                     vbr = a.diag_mode == 0 ? cfma(coefc, csub(ubase, y0), unx) : cfms(coefc, y0, unx);
                     ubase_prev = ubase;
                     ubase = unx;
