@@ -384,7 +384,7 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     HP_CUDA(cudaGetDevice(&dev));
     HP_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     // variants: 0 automatic; 1 direct (global loads); 2 staged, block-synchronous phases; 3 pipelined (csrc/hp_sweep2.cu)
-    bool pipe_ok = L.CW <= HP2_OFF_COLS && 2 * s->b <= 64 && L.NR <= 128 && s->mleaf && hp_sweep2_smem(L, s->b) + 1024 <= (size_t)max_smem;
+    bool pipe_ok = L.K <= 16 && L.CW <= HP2_OFF_COLS && 2 * s->b <= 64 && L.NR <= 128 && s->mleaf && hp_sweep2_smem(L, s->b) + 1024 <= (size_t)max_smem;
     bool tma_ok = 2 * stage + small + 1024 <= (size_t)max_smem;
     int variant = s->sweep_variant;
     if (variant == 0) variant = pipe_ok ? 3 : (tma_ok ? 2 : 1);

@@ -150,26 +150,39 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
             if (a.dbg && tid == 0) tprev = clock64();
             // ---- C1: the leaf's first CTA turns the partial gb into GR(t) = sum gb + M(t) x(t-1)
             if (reducer && cw == 0) {
-                if (it > 0) {
+                // one batch of loads per lane: its x(t-1) word and the K partial gb words (one L2 round trip when ready)
+                cplx gsum[HP2_KPL];
 #pragma unroll
-                    for (int i = 0; i < HP2_KPL; ++i) {
-                        int t = lane + 32 * i;
-                        if (t < b2) {
-                            int side = t / b, kap = t - side * b, j = l - 1 + side;
-                            xlr_c[t] = (j >= 0 && j < P - 1) ? xwait(slot_prev + a.oXS + (size_t)j * b + kap, abort_flag, dead) : cmake(0.0, 0.0);
+                for (int i = 0; i < HP2_KPL; ++i) {
+                    const int t = lane + 32 * i;
+                    gsum[i] = cmake(0.0, 0.0);
+                    if (t < b2) {
+                        const int side = t / b, kap = t - side * b, j = l - 1 + side;
+                        const bool need_x = it > 0 && j >= 0 && j < P - 1;
+                        const cplx* px = slot_prev + a.oXS + (size_t)j * b + kap;
+                        cplx xv = cmake(0.0, 0.0), gv[16];
+                        unsigned int spins = 0;
+                        for (;;) {
+                            bool ok = true;
+                            if (need_x) ok = xtry(px, xv);
+                            for (int kk = 0; kk < K; ++kk) ok = xtry(slot + a.oGP + (size_t)(g + kk) * b2 + t, gv[kk & 15]) && ok;
+                            if (ok || *dead) break;
+                            if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; break; }
+                            if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) { *dead = 1u; break; }
                         }
+                        xlr_c[t] = xv;
+                        for (int kk = 0; kk < K; ++kk) gsum[i] = cadd(gsum[i], gv[kk & 15]);
                     }
-                    __syncwarp();
-                    mbar_wait(&mbar[4 + (it & 1)], (it >> 1) & 1);
                 }
+                __syncwarp();
+                if (it > 0) mbar_wait(&mbar[4 + (it & 1)], (it >> 1) & 1);
                 HP_TICK(0);
                 const cplx* M = reinterpret_cast<const cplx*>(ringM + (it & 1) * m_st);
 #pragma unroll
                 for (int i = 0; i < HP2_KPL; ++i) {
                     int kp = lane + 32 * i;
                     if (kp < b2) {
-                        cplx acc = cmake(0.0, 0.0);
-                        for (int kk = 0; kk < K; ++kk) acc = cadd(acc, xwait(slot + a.oGP + (size_t)(g + kk) * b2 + kp, abort_flag, dead));
+                        cplx acc = gsum[i];
                         if (it > 0) {
                             cplx a1 = cmake(0.0, 0.0), a2 = cmake(0.0, 0.0), a3 = cmake(0.0, 0.0);
                             int kap = 0;
