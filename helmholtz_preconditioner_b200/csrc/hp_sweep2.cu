@@ -46,7 +46,11 @@ __device__ __forceinline__ void ring_fill(unsigned char* dst, const cplx* src, u
         bulk_g2s(dst + o, (const char*)src + o, min(HP_BULK_CHUNK, bytes - o), bar);
 }
 
+// MODE: 0 forward, 1 backward (reference diagonal), 2 backward (paper diagonal), 3 single strip apply
+template <int MODE, bool DBG>
 __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
+    constexpr int a_mode = MODE == 0 ? 0 : (MODE == 3 ? 2 : 1);
+    constexpr int a_diag = MODE == 2 ? 1 : 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = a.b, b2 = 2 * a.b, n = a.n, K = a.lay.K, P = a.lay.P, G = a.lay.G, QP = a.lay.QP, CW = a.lay.CW;
     const int NS = a.lay.NS, NSP = a.lay.NSP, NR = a.lay.NR;
@@ -56,10 +60,10 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
     const int lc0 = (q * k) / K, lc1 = (q * (k + 1)) / K, ncols = lc1 - lc0, c0 = ls + lc0;
     const int row0 = g * NR, nrows = max(0, min(NR, NS - row0));
     unsigned int* abort_flag = a.bar + 1;
-    const int step = a.mode == 1 ? -1 : 1;
-    const int nsteps = a.mode == 2 ? 1 : (a.mode == 0 ? a.m_to - a.m_from + 1 : a.m_from - a.m_to + 1);
-    const int dir = a.mode == 1 ? 1 : 0;
-    const double sg = a.diag_mode == 0 ? 1.0 : -1.0;
+    const int step = a_mode == 1 ? -1 : 1;
+    const int nsteps = a_mode == 2 ? 1 : (a_mode == 0 ? a.m_to - a.m_from + 1 : a.m_from - a.m_to + 1);
+    const int dir = a_mode == 1 ? 1 : 0;
+    const double sg = a_diag == 0 ? 1.0 : -1.0;
 
     // ---- shared memory carve-up (must match hp_sweep2_smem)
     const unsigned int wg_bytes = (unsigned int)(a.lay.offN * sizeof(cplx));
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
         // =====================================================================================================
         const int ctid = tid, cw = ctid >> 5;
         long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
-#define HP_TICK(i) do { if (a.dbg && lane == 0 && (tid == 0 || tid == HP2_CRIT)) { long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
+#define HP_TICK(i) do { if (DBG && lane == 0 && (tid == 0 || tid == HP2_CRIT)) { long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
         if (ctid == 0) {
             for (int sidx = 0; sidx < 2 && sidx < nsteps; ++sidx) {
                 int ms = m0 + sidx * step;
@@ -122,8 +126,8 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
         cplx usbase = cmake(0.0, 0.0);
         if (sep_col >= 0) {                                    // input value of the first strip on the separator column
             cplx v;
-            if (a.mode == 2) v = a.vin[sep_col];
-            else if (a.mode == 0) v = ldcg(a.u + (size_t)(m0 - 1) * n + sep_col);
+            if (a_mode == 2) v = a.vin[sep_col];
+            else if (a_mode == 0) v = ldcg(a.u + (size_t)(m0 - 1) * n + sep_col);
             else {
                 usbase = ldcg(a.u + (size_t)(m0 - 1) * n + sep_col);
                 v = usbase;
@@ -143,16 +147,16 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
             // early loads for the separator column of this lane
             cplx usep = cmake(0.0, 0.0), rfac = cmake(0.0, 0.0);
             if (sep_col >= 0) {
-                rfac = hp_rowfac(a, a.mode == 1 ? mn : m);
-                if (a.mode == 0) usep = ldcg(a.u + (size_t)m * n + sep_col);
-                else if (a.mode == 1 && more) usep = ldcg(a.u + (size_t)(mn - 1) * n + sep_col);
+                rfac = hp_rowfac(a, a_mode == 1 ? mn : m);
+                if (a_mode == 0) usep = ldcg(a.u + (size_t)m * n + sep_col);
+                else if (a_mode == 1 && more) usep = ldcg(a.u + (size_t)(mn - 1) * n + sep_col);
             }
-            if (a.dbg && tid == 0) tprev = clock64();
+            if (DBG && tid == 0) tprev = clock64();
             // ---- C1: the leaf's first CTA turns the partial gb into GR(t) = sum gb + M(t) x(t-1)
             if (reducer && cw == 0) {
                 // one batch of loads per lane: its x(t-1) word and the K partial gb words (one L2 round trip when ready)
                 cplx gsum[HP2_KPL];
-#pragma unroll
+#pragma unroll 1
                 for (int i = 0; i < HP2_KPL; ++i) {
                     const int t = lane + 32 * i;
                     gsum[i] = cmake(0.0, 0.0);
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 if (it > 0) mbar_wait(&mbar[4 + (it & 1)], (it >> 1) & 1);
                 HP_TICK(0);
                 const cplx* M = reinterpret_cast<const cplx*>(ringM + (it & 1) * m_st);
-#pragma unroll
+#pragma unroll 1
                 for (int i = 0; i < HP2_KPL; ++i) {
                     int kp = lane + 32 * i;
                     if (kp < b2) {
@@ -261,13 +265,13 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                         xput(slot + a.oXS + row0 + rr, acc);
                         xarm(slot_arm + a.oXS + row0 + rr);
                         if (sep_col >= 0) {                                             // y_s = x_s[b-1]
-                            if (a.mode == 2) a.yout[sep_col] = acc;
-                            else if (a.mode == 0) {
+                            if (a_mode == 2) a.yout[sep_col] = acc;
+                            else if (a_mode == 0) {
                                 cplx un = cfms(cmul(rfac, cis1s), acc, usep);
                                 a.u[(size_t)m * n + sep_col] = un;
                                 if (more) xput(slot_next + a.oVS + sep_j, un);
                             } else {
-                                cplx un = a.diag_mode == 0 ? csub(usbase, acc) : acc;
+                                cplx un = a_diag == 0 ? csub(usbase, acc) : acc;
                                 a.u[(size_t)(m - 1) * n + sep_col] = un;
                                 if (more) xput(slot_next + a.oVS + sep_j, cfma(cscale(sg, cmul(rfac, cis1s)), un, usep));
                                 usbase = usep;
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                               &mbar[2 + (it & 1)]);
             }
         }
-        if (a.dbg && tid == 0)
+        if (DBG && tid == 0)
             for (int i = 0; i < 8; ++i) a.dbg[(size_t)g * 16 + i] = tacc[i];
     } else {
         // =====================================================================================================
@@ -308,8 +312,8 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
         cplx vbr = cmake(0.0, 0.0), y0prev = cmake(0.0, 0.0), coefc = cmake(0.0, 0.0), ubase = cmake(0.0, 0.0),
              ubase_prev = cmake(0.0, 0.0);
         if (col) {
-            if (a.mode == 2) vbr = a.vin[c];
-            else if (a.mode == 0) vbr = ldcg(a.u + (size_t)(m0 - 1) * n + c);
+            if (a_mode == 2) vbr = a.vin[c];
+            else if (a_mode == 0) vbr = ldcg(a.u + (size_t)(m0 - 1) * n + c);
             else {
                 ubase = ldcg(a.u + (size_t)(m0 - 1) * n + c);
                 vbr = ubase;
@@ -329,13 +333,13 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
             const cplx* Wp = pk;
             const cplx* Gp = pk + a.lay.offG;
             // early loads: the row coupling and the field value vb(t+1) is built from (written by no other thread)
-            const cplx rf_it = hp_rowfac(a, a.mode == 1 ? mn : m);
+            const cplx rf_it = hp_rowfac(a, a_mode == 1 ? mn : m);
             cplx unx = cmake(0.0, 0.0);
             if (col && live) {
-                if (a.mode == 0) unx = ldcg(a.u + (size_t)m * n + c);
-                else if (a.mode == 1 && more) unx = ldcg(a.u + (size_t)(mn - 1) * n + c);
+                if (a_mode == 0) unx = ldcg(a.u + (size_t)m * n + c);
+                else if (a_mode == 1 && more) unx = ldcg(a.u + (size_t)(mn - 1) * n + c);
             }
-            if (a.dbg && ot == 0) tprev = clock64();
+            if (DBG && ot == 0) tprev = clock64();
             // ---- a: gb(t) = Gc(t) vb(t)
             if (live) {
                 mbar_wait(&mbar[it & 1], (it >> 1) & 1);
@@ -378,10 +382,10 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                     for (; kap < b2; ++kap) corr = cfma(Gprev[(size_t)kap * CW + ot], xlr_o[kap], corr);
                     corr = cadd(cadd(corr, c1), cadd(c2, c3));
                     v = cfma(coefc, corr, vbr);
-                    if (a.mode == 2) a.yout[c] = csub(y0prev, corr);
-                    else if (a.mode == 0) a.u[(size_t)mp * n + c] = v;                      // row m_{t-1}: final
+                    if (a_mode == 2) a.yout[c] = csub(y0prev, corr);
+                    else if (a_mode == 0) a.u[(size_t)mp * n + c] = v;                      // row m_{t-1}: final
                     else {
-                        cplx un = a.diag_mode == 0 ? cadd(csub(ubase_prev, y0prev), corr) : csub(y0prev, corr);
+                        cplx un = a_diag == 0 ? cadd(csub(ubase_prev, y0prev), corr) : csub(y0prev, corr);
                         a.u[(size_t)(mp - 1) * n + c] = un;
                     }
                 }
@@ -428,12 +432,12 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
 #pragma unroll
                 for (int w = 1; w < 8; ++w) y0 = cadd(y0, y0w[(size_t)w * CW + ot]);
                 y0prev = y0;
-                if (a.mode == 0) {
+                if (a_mode == 0) {
                     coefc = cmul(rf_it, cis1);                                 // A_{m+1,m}
                     vbr = cfms(coefc, y0, unx);                                // u_{m+1} - coef y0
-                } else if (a.mode == 1) {
+                } else if (a_mode == 1) {
                     coefc = cmul(rf_it, cis1);                                 // A_{m-1,m}
-                    vbr = a.diag_mode == 0 ? cfma(coefc, csub(ubase, y0), unx) : cfms(coefc, y0, unx);
+                    vbr = a_diag == 0 ? cfma(coefc, csub(ubase, y0), unx) : cfms(coefc, y0, unx);
                     ubase_prev = ubase;
                     ubase = unx;
                 }
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
             bar_off();                                   // vb, y0w free for the next strip
             HP_TICK(6);
         }
-        if (a.dbg && ot == 0)
+        if (DBG && ot == 0)
             for (int i = 0; i < 8; ++i) a.dbg[(size_t)g * 16 + 8 + i] = tacc[i];
     }
 }
@@ -457,8 +461,14 @@ size_t hp_sweep2_smem(const HpLayout& L, int b) {
 int hp_sweep2_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st) {
     const HpLayout& L = s->lay;
     size_t smem = hp_sweep2_smem(L, s->b);
-    HP_CUDA(cudaFuncSetAttribute(hp_sweep2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int mode = a.mode == 0 ? 0 : (a.mode == 2 ? 3 : (a.diag_mode == 0 ? 1 : 2));
+    const void* fns[2][4] = {{(const void*)hp_sweep2_kernel<0, false>, (const void*)hp_sweep2_kernel<1, false>,
+                              (const void*)hp_sweep2_kernel<2, false>, (const void*)hp_sweep2_kernel<3, false>},
+                             {(const void*)hp_sweep2_kernel<0, true>, (const void*)hp_sweep2_kernel<1, true>,
+                              (const void*)hp_sweep2_kernel<2, true>, (const void*)hp_sweep2_kernel<3, true>}};
+    const void* fn = fns[a.dbg ? 1 : 0][mode];
+    HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {&a};
-    HP_CUDA(cudaLaunchCooperativeKernel((const void*)hp_sweep2_kernel, dim3(L.G), dim3(HP2_THREADS), args, smem, st));
+    HP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.G), dim3(HP2_THREADS), args, smem, st));
     return 0;
 }
