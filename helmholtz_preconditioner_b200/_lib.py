@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhelmholtz_b200.so")
+LIB_PATH = os.environ.get("HELMHOLTZ_B200_LIB", os.path.join(HERE, "libhelmholtz_b200.so"))   # env override: developer builds
 
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _ip = C.POINTER(C.c_int)
