@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                     }
                 }
                 __syncwarp();
-                if (it > 0) mbar_wait(&mbar[4 + (it & 1)], (it >> 1) & 1);
+                // (also at it = 0, where M is not used: the stage must have landed before it is refilled below)
+                mbar_wait(&mbar[4 + (it & 1)], (it >> 1) & 1);
                 HP_TICK(0);
                 const cplx* M = reinterpret_cast<const cplx*>(ringM + (it & 1) * m_st);
 #pragma unroll 1
