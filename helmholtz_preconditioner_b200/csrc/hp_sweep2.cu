@@ -25,6 +25,8 @@
 #define HP2_THREADS (HP2_CRIT + HP2_OFF)
 #define HP2_KPL 2            // interface components per lane of a warp: 2b <= 64
 
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define HP_STAMP(k) do { if (DBG && it >= 512 && it < 576) a.dbg[(size_t)G * 16 + ((size_t)g * 64 + (it - 512)) * 4 + (k)] = (long long)gtime(); } while (0)
 __device__ __forceinline__ void bar_crit() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void bar_off() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                         for (int kk = 0; kk < K; ++kk) gsum[i] = cadd(gsum[i], gv[kk & 15]);
                     }
                 }
+                if (lane == 0) HP_STAMP(0);
                 __syncwarp();
                 // (also at it = 0, where M is not used: the stage must have landed before it is refilled below)
                 mbar_wait(&mbar[4 + (it & 1)], (it >> 1) & 1);
@@ -206,6 +209,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                     }
                 }
                 __syncwarp();
+                if (lane == 0) HP_STAMP(1);
                 HP_TICK(1);
                 if (lane == 0 && it + 2 < nsteps)
                     ring_fill(ringM + (it & 1) * m_st, m_base + (size_t)(m + 2 * step - a.m_lo) * m_stride, m_bytes, &mbar[4 + (it & 1)]);
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 }
                 HP_TICK(2);
                 bar_crit();
+                if (ctid == 0) HP_STAMP(2);
                 mbar_wait(&mbar[2 + (it & 1)], (it >> 1) & 1);
                 HP_TICK(3);
                 const cplx* Np = reinterpret_cast<const cplx*>(ringN + (it & 1) * n_st);
@@ -282,6 +287,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                     }
                 }
                 bar_crit();
+                if (ctid == 0) HP_STAMP(3);
                 HP_TICK(4);
                 if (ctid == 0 && it + 2 < nsteps)
                     ring_fill(ringN + (it & 1) * n_st, pk_base + (size_t)(m + 2 * step - a.m_lo) * strip_stride + a.lay.offN, n_bytes,
