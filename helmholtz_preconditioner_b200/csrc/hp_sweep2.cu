@@ -211,6 +211,21 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                 __syncwarp();
                 if (lane == 0) HP_STAMP(1);
                 HP_TICK(1);
+                if (DBG && tid == 0) {          // in-situ latencies: one L2 round trip of an exchange word, one smem load
+                    cplx tmp;
+                    long long c0_ = clock64();
+                    bool okk = xtry(slot + a.oGR + (size_t)l * b2, tmp);
+                    long long c1_ = clock64();
+                    if (okk && tmp.x == 12345.678) tacc[7] += 1;
+                    tacc[5] += c1_ - c0_;
+                    volatile cplx* vp = xlr_c;
+                    long long c2_ = clock64();
+                    double q_ = vp[0].x;
+                    long long c3_ = clock64();
+                    if (q_ == 12345.678) tacc[7] += 1;
+                    tacc[6] += c3_ - c2_;
+                    tprev = clock64();
+                }
                 if (lane == 0 && it + 2 < nsteps)
                     ring_fill(ringM + (it & 1) * m_st, m_base + (size_t)(m + 2 * step - a.m_lo) * m_stride, m_bytes, &mbar[4 + (it & 1)]);
             }

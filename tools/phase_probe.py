@@ -23,10 +23,11 @@ for variant in (3, 2):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); s.sweep_forward(u, b + 1, n - 1); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    out = np.zeros((L["G"], 16), dtype=np.int64)
-    s.lib.hp_debug_phases(s.handle, 0, out.ctypes.data)
+    raw = np.zeros(L["G"] * (16 + 256), dtype=np.int64)
+    s.lib.hp_debug_phases(s.handle, 0, raw.ctypes.data)
+    out = raw[:L["G"] * 16].reshape(L["G"], 16) if variant == 3 else np.pad(raw[:L["G"] * 8].reshape(L["G"], 8), ((0, 0), (0, 8)))
     nst = n - 1 - b
-    names = (["C1 wait xs", "C1 gpb+M", "C2 wait GR", "C2 bar+N", "C2 rows", "-", "-", "-", "a tma", "a gb", "b wait xs", "b corr", "c gather", "c W", "c tail", "-"]
+    names = (["C1 wait xs", "C1 gpb+M", "C2 wait GR", "C2 bar+N", "C2 rows", "L2 RT", "LDS", "-", "a tma", "a gb", "b wait xs", "b corr", "c gather", "c W", "c tail", "-"]
              if variant == 3 else ["tma_wait", "S1", "reduce_wait", "S2_poll", "S2_compute", "S3_poll", "S3"])
     print(f"variant {variant}: {ms:.2f} ms, {1e3 * ms / nst:.2f} us/strip; cycles/strip (mean over CTAs | min | max):")
     for i, nm in enumerate(names):
