@@ -58,6 +58,7 @@ struct hp_solver {
     int *leaf_start = nullptr, *leaf_q = nullptr, *sep = nullptr;   // device copies
     cplx* packets = nullptr;
     cplx* mleaf = nullptr;        // transfer matrices of the pipelined sweep: [strip][dir][leaf][2b][2b]
+    cplx* qmat = nullptr;         // one-hop recurrence matrices Q = N Mrho: [strip][dir][G][NR][NSP]
     int64_t bytes = 0;
     double setup_ms = 0.0;
     // front block: Thomas factors of the b tridiagonal diagonal blocks (reference H_F)

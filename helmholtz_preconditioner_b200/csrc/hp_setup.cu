@@ -160,6 +160,65 @@ __global__ void __launch_bounds__(256) hp_mleaf_kernel(const cplx* __restrict__ 
     }
 }
 
+// One-hop form of the separator recurrence (csrc/hp_sweep3.cu).  With rho(t) = rho_b(t) - Mrho(t) x(t-1), where
+// Mrho is block tridiagonal over the separators,
+//   block (j+1, j) = M_{j+1}[Gl rows, left cols]                                   (leaf j+1 lies left of separator j+1)
+//   block (j,   j) = M_j[Gl rows, right cols] + M_{j+1}[Gf rows, left cols] + cs_j e_b e_b^T
+//   block (j-1, j) = M_j[Gf rows, right cols]
+// (cs_j = coupling of the separator column between the two grid rows of the pair), the separator solution obeys
+//   x(t) = N rho_b(t) - Q(t) x(t-1),   Q = N Mrho   dense [(P-1)b]^2, rows distributed over the CTAs like N:
+//   qmat[((m-m_lo)*2 + dir)*G + g][NR][NSP].      CTA -> (strip, dir, g); threads over the columns of Q.
+__global__ void __launch_bounds__(256) hp_q_kernel(const cplx* __restrict__ packets, const cplx* __restrict__ mleaf, HpLayout lay,
+        const int* __restrict__ sep, int m_lo, int m_hi, int b, double ih2, const cplx* __restrict__ s2t,
+        const cplx* __restrict__ is1t, cplx* __restrict__ qmat) {
+    extern __shared__ double2 sm[];
+    const int G = lay.G, P = lay.P, NS = lay.NS, NSP = lay.NSP, NR = lay.NR, b2 = 2 * b, ns = P - 1;
+    const int g = blockIdx.x % G, dir = (blockIdx.x / G) & 1, mi = blockIdx.x / (2 * G);
+    const int m = m_lo + mi, mprev = dir == 0 ? m - 1 : m + 1;
+    if (mprev < m_lo || mprev > m_hi) return;
+    const int row0 = g * NR, nrows = max(0, min(NR, NS - row0));
+    if (nrows == 0) return;
+    const cplx* Np = packets + ((size_t)mi * G + g) * lay.PK + lay.offN;
+    cplx* Ns = sm;                                    // [NR][NS]
+    for (int e = threadIdx.x; e < nrows * NS; e += blockDim.x) Ns[e] = Np[(size_t)(e / NS) * NSP + (e % NS)];
+    __syncthreads();
+    const cplx* ML = mleaf + (size_t)(mi * 2 + dir) * P * b2 * b2;       // M_l(m, dir), stored transposed [col][row]
+    const cplx rf = cscale(ih2, s2t[2 * (dir == 0 ? m - 1 : m) + 1]);
+    cplx* out = qmat + ((size_t)(mi * 2 + dir) * G + g) * NR * NSP;
+    for (int col = threadIdx.x; col < NS; col += blockDim.x) {
+        const int j = col / b, kap = col - j * b;
+        const cplx* Mj = ML + (size_t)j * b2 * b2;                        // leaf j   (left of separator j)
+        const cplx* Mj1 = ML + (size_t)(j + 1) * b2 * b2;                 // leaf j+1 (right of separator j)
+        const cplx cs = cmul(rf, is1t[2 * (sep[j] + 1)]);
+        for (int r0 = 0; r0 < nrows; r0 += 4) {
+            cplx acc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = cmake(0.0, 0.0);
+            for (int kp = 0; kp < b; ++kp) {
+                // Mrho[(jp,kp)][(j,kap)] for jp = j-1, j, j+1 ; M_l[r][c] = stored[c*2b + r]
+                cplx m_lo_blk = j > 0 ? Mj[(size_t)(b + kap) * b2 + kp] : cmake(0.0, 0.0);                   // (j-1, j): M_j[kp][b+kap]
+                cplx m_di_blk = cadd(Mj[(size_t)(b + kap) * b2 + b + kp], Mj1[(size_t)kap * b2 + kp]);       // (j, j)
+                if (kp == b - 1 && kap == b - 1) m_di_blk = cadd(m_di_blk, cs);
+                cplx m_hi_blk = j + 1 < ns ? Mj1[(size_t)kap * b2 + b + kp] : cmake(0.0, 0.0);               // (j+1, j): M_{j+1}[b+kp][kap]
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (r0 + i < nrows) {
+                        const cplx* nr = Ns + (size_t)(r0 + i) * NS;
+                        cplx a_ = acc[i];
+                        if (j > 0) a_ = cfma(nr[(j - 1) * b + kp], m_lo_blk, a_);
+                        a_ = cfma(nr[j * b + kp], m_di_blk, a_);
+                        if (j + 1 < ns) a_ = cfma(nr[(j + 1) * b + kp], m_hi_blk, a_);
+                        acc[i] = a_;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (r0 + i < nrows) out[(size_t)(r0 + i) * NSP + col] = acc[i];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // partition
 // ------------------------------------------------------------------------------------------------------
@@ -211,6 +270,7 @@ static int hp_choose_layout(hp_solver* s, int nstrips, int P_req, int K_req, HpL
 void hp_free_strips(hp_solver* s) {
     cudaFree(s->packets); s->packets = nullptr;
     cudaFree(s->mleaf); s->mleaf = nullptr;
+    cudaFree(s->qmat); s->qmat = nullptr;
     cudaFree(s->leaf_start); s->leaf_start = nullptr;
     cudaFree(s->leaf_q); s->leaf_q = nullptr;
     cudaFree(s->sep); s->sep = nullptr;
@@ -310,6 +370,20 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
                                                                             1.0 / (s->pml.h * s->pml.h), s->s2t, s->is1t, s->mleaf);
         HP_CUDA(cudaGetLastError());
         s->bytes += (int64_t)mbytes;
+        // one-hop recurrence matrices Q = N Mrho (skipped when memory is short: the sweep then uses the two-hop kernel)
+        size_t qbytes = (size_t)nstrips * 2 * L.G * L.NR * L.NSP * sizeof(cplx);
+        size_t free_q = 0, total_q = 0;
+        cudaMemGetInfo(&free_q, &total_q);
+        if (L.NS > 0 && qbytes + ((size_t)8 << 30) < free_q) {
+            HP_CUDA(cudaMalloc(&s->qmat, qbytes));
+            HP_CUDA(cudaMemsetAsync(s->qmat, 0, qbytes, st));
+            size_t qsm = sizeof(cplx) * (size_t)L.NR * L.NS;
+            if (qsm > 48 * 1024) HP_CUDA(cudaFuncSetAttribute(hp_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsm));
+            hp_count_launch(); hp_q_kernel<<<nstrips * 2 * L.G, 256, qsm, st>>>(s->packets, s->mleaf, L, s->sep, m_lo, m_hi, b,
+                                                                             1.0 / (s->pml.h * s->pml.h), s->s2t, s->is1t, s->qmat);
+            HP_CUDA(cudaGetLastError());
+            s->bytes += (int64_t)qbytes;
+        }
     }
     cudaEventRecord(e1, st);
     HP_CUDA(cudaStreamSynchronize(st));

@@ -352,6 +352,8 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
 #define HP2_OFF_COLS 256
 size_t hp_sweep2_smem(const HpLayout& L, int b);
 int hp_sweep2_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st);
+size_t hp_sweep3_smem(const HpLayout& L, int b);
+int hp_sweep3_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st);
 
 int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout, int m_from, int m_to,
                     int diag_mode, cudaStream_t st) {
@@ -367,7 +369,7 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     HpSweepArgs a;
     a.n = s->n; a.b = s->b; a.lay = s->lay;
     a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
-    a.packets = s->packets; a.mleaf = s->mleaf; a.m_lo = s->m_lo;
+    a.packets = s->packets; a.mleaf = s->mleaf; a.qmat = s->qmat; a.m_lo = s->m_lo;
     a.mode = mode; a.m_from = m_from; a.m_to = m_to; a.diag_mode = diag_mode;
     a.u = u; a.vin = vin; a.yout = yout;
     a.xch = s->xch; a.bar = s->bar;
@@ -383,18 +385,23 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     int max_smem = 0, dev = 0;
     HP_CUDA(cudaGetDevice(&dev));
     HP_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    // variants: 0 automatic; 1 direct (global loads); 2 staged, block-synchronous phases; 3 pipelined (csrc/hp_sweep2.cu)
+    // variants: 0 automatic; 1 direct (global loads); 2 staged, block-synchronous phases; 3 pipelined, two hand-overs per
+    // strip (csrc/hp_sweep2.cu); 4 pipelined, one hand-over per strip (csrc/hp_sweep3.cu)
     bool pipe_ok = L.K <= 16 && L.CW <= HP2_OFF_COLS && 2 * s->b <= 64 && L.NR <= 128 && s->mleaf && hp_sweep2_smem(L, s->b) + 1024 <= (size_t)max_smem;
     bool tma_ok = 2 * stage + small + 1024 <= (size_t)max_smem;
+    bool hop1_ok = pipe_ok && s->qmat && L.NS > 0 && hp_sweep3_smem(L, s->b) + 1024 <= (size_t)max_smem;
     int variant = s->sweep_variant;
-    if (variant == 0) variant = pipe_ok ? 3 : (tma_ok ? 2 : 1);
+    if (variant == 0) variant = hop1_ok ? 4 : (pipe_ok ? 3 : (tma_ok ? 2 : 1));
+    if (variant == 4 && !hop1_ok) variant = 3;
     if (variant == 3 && !pipe_ok) variant = tma_ok ? 2 : 1;
     if (variant == 2 && !tma_ok) variant = 1;
     // the exchange ring starts all-sentinel (0xFF bytes); bar[1] = abort flag
     HP_CUDA(cudaMemsetAsync(s->xch, 0xFF, sizeof(cplx) * HP_RING * a.slot_stride, st));
     hp_count_launch();
     hp_profile_begin(s, st);
-    if (variant == 3) {
+    if (variant == 4) {
+        if (hp_sweep3_launch(s, a, st)) return 2;
+    } else if (variant == 3) {
         if (hp_sweep2_launch(s, a, st)) return 2;
     } else {
         bool tma = variant == 2;

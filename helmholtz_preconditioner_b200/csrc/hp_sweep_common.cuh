@@ -11,6 +11,7 @@ struct HpSweepArgs {
     const int *leaf_start, *leaf_q, *sep;
     const cplx* packets;
     const cplx* mleaf;        // transfer matrices [strip][dir][leaf][2b][2b] (pipelined kernel)
+    const cplx* qmat;         // one-hop recurrence matrices [strip][dir][G][NR][NSP]
     int m_lo;
     int mode, m_from, m_to, diag_mode;
     cplx* u;

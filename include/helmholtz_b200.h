@@ -68,8 +68,8 @@ int hp_precond_setup(hp_solver* s, int P, int K, int m_lo, int m_hi, void* strea
 /* bytes of device memory held by the strip factorisation, and the device time the last setup took */
 int64_t hp_precond_bytes(hp_solver* s);
 double hp_precond_setup_ms(hp_solver* s);
-/* sweep kernel variant: 0 = automatic, 1 = direct loads, 2 = TMA-staged block-synchronous, 3 = pipelined (default
- * when its shared-memory rings fit) */
+/* sweep kernel variant: 0 = automatic, 1 = direct loads, 2 = TMA-staged block-synchronous, 3 = pipelined with two
+ * hand-overs per strip, 4 = pipelined with one hand-over per strip (default when its rings and matrices fit) */
 int hp_set_sweep_variant(hp_solver* s, int variant);
 /* 0 = fine; 1 = a sweep kernel gave up waiting for data from another CTA (a bug, never expected); synchronises */
 int hp_sweep_status(hp_solver* s);

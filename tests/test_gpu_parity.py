@@ -99,7 +99,7 @@ def test_strip_apply_vs_oracle(hp, n, b, P, K):
     Pc = orc.SweepingPreconditioner(b, 60.0, b * h, omega, h, n, c_mat)
     s = hp.HelmholtzSolver(n, b, omega, 60.0, c_mat).setup_preconditioner(P=P, K=K)
     rng = np.random.default_rng(3)
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         s.set_sweep_variant(variant)
         for m in (b + 1, (n + b) // 2, n - 1, n):
             v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
@@ -184,7 +184,7 @@ def test_medium_preconditioner_vs_oracle(hp):
     Pc.diag = "paper"
     Pc_paper = Pc.apply(f)
     assert relerr(hp.algo2_4(f, b, n, s), ref) < 1e-12
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         s.set_sweep_variant(variant)
         assert relerr(hp.algo2_4(f, b, n, s), ref) < 1e-12
         assert relerr(hp.algo2_4(f, b, n, s, diag="paper"), Pc_paper) < 1e-12

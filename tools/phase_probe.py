@@ -15,7 +15,7 @@ s.setup_preconditioner(P=P, K=K)
 L = s.layout()
 print({k: int(L[k]) for k in ("P", "K", "G", "QP", "CW", "NS", "NR", "PK")}, "setup ms", s.setup_ms)
 u = torch.from_numpy(f_mat.ravel().astype(np.complex128)).cuda()
-for variant in (3, 2):
+for variant in (4, 3):
     s.set_sweep_variant(variant)
     s.sweep_forward(u, b + 1, n - 1)
     torch.cuda.synchronize()
@@ -25,14 +25,14 @@ for variant in (3, 2):
     ms = e0.elapsed_time(e1)
     raw = np.zeros(L["G"] * (16 + 256), dtype=np.int64)
     s.lib.hp_debug_phases(s.handle, 0, raw.ctypes.data)
-    out = raw[:L["G"] * 16].reshape(L["G"], 16) if variant == 3 else np.pad(raw[:L["G"] * 8].reshape(L["G"], 8), ((0, 0), (0, 8)))
+    out = raw[:L["G"] * 16].reshape(L["G"], 16) if variant >= 3 else np.pad(raw[:L["G"] * 8].reshape(L["G"], 8), ((0, 0), (0, 8)))
     nst = n - 1 - b
     names = (["C1 wait xs", "C1 gpb+M", "C2 wait GR", "C2 bar+N", "C2 rows", "L2 RT", "LDS", "-", "a tma", "a gb", "b wait xs", "b corr", "c gather", "c W", "c tail", "-"]
-             if variant == 3 else ["tma_wait", "S1", "reduce_wait", "S2_poll", "S2_compute", "S3_poll", "S3"])
+             if variant >= 3 else ["tma_wait", "S1", "reduce_wait", "S2_poll", "S2_compute", "S3_poll", "S3"])
     print(f"variant {variant}: {ms:.2f} ms, {1e3 * ms / nst:.2f} us/strip; cycles/strip (mean over CTAs | min | max):")
     for i, nm in enumerate(names):
         print(f"   {nm:9s} {out[:, i].mean() / nst:9.0f} {out[:, i].min() / nst:9.0f} {out[:, i].max() / nst:9.0f}")
     red = np.arange(L["G"]) % L["K"] == 0
-    if variant == 3:
+    if variant >= 3:
         print("   reducers only: C1 wait xs %.0f  C1 gpb+M %.0f  C2 wait GR %.0f" % tuple(out[red, i].mean() / nst for i in (0, 1, 2)))
     print("   total     ", out[:, :8].sum(1).mean() / nst, out[:, 8:].sum(1).mean() / nst, "status", s.lib.hp_sweep_status(s.handle))
