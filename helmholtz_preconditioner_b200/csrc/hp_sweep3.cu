@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep3_kernel(HpSweepArgs a) {
                 {
                     const int item = 2 * it;
                     mbar_wait(&mbar[2 + item % 3], (item / 3) & 1);
+                    HP_TICK(5);
                     const cplx* Np = reinterpret_cast<const cplx*>(ringN + (item % 3) * n_st);
                     for (int o = 0; cw + 4 * o < nrows; ++o) {
                         const cplx* nr = Np + (size_t)(cw + 4 * o) * NSP;
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep3_kernel(HpSweepArgs a) {
                 {
                     const int item = 2 * it + 1;
                     mbar_wait(&mbar[2 + item % 3], (item / 3) & 1);          // (also at it = 0: it has to land before the refill)
+                    HP_TICK(6);
                     const cplx* Qp = reinterpret_cast<const cplx*>(ringN + (item % 3) * n_st);
                     for (int o = 0; cw + 4 * o < nrows; ++o) {
                         const int rr = cw + 4 * o;
@@ -294,6 +296,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep3_kernel(HpSweepArgs a) {
                         }
                     }
                 }
+                HP_TICK(7);
                 bar_crit();                                  // every warp is done with the Q slot
                 HP_TICK(4);
                 if (ctid == 0 && 2 * it + 4 < nitems) ring_fill(ringN + ((2 * it + 1) % 3) * n_st, item_src(2 * it + 4), n_bytes, &mbar[2 + (2 * it + 1) % 3]);

@@ -15,7 +15,7 @@ s.setup_preconditioner(P=P, K=K)
 L = s.layout()
 print({k: int(L[k]) for k in ("P", "K", "G", "QP", "CW", "NS", "NR", "PK")}, "setup ms", s.setup_ms)
 u = torch.from_numpy(f_mat.ravel().astype(np.complex128)).cuda()
-for variant in (4, 3):
+for variant in (tuple(int(v) for v in sys.argv[5].split(",")) if len(sys.argv) > 5 else (3,)):
     s.set_sweep_variant(variant)
     s.sweep_forward(u, b + 1, n - 1)
     torch.cuda.synchronize()
@@ -27,7 +27,7 @@ for variant in (4, 3):
     s.lib.hp_debug_phases(s.handle, 0, raw.ctypes.data)
     out = raw[:L["G"] * 16].reshape(L["G"], 16) if variant >= 3 else np.pad(raw[:L["G"] * 8].reshape(L["G"], 8), ((0, 0), (0, 8)))
     nst = n - 1 - b
-    names = (["C1 wait xs", "C1 gpb+M", "C2 wait GR", "C2 bar+N", "C2 rows", "L2 RT", "LDS", "-", "a tma", "a gb", "b wait xs", "b corr", "c gather", "c W", "c tail", "-"]
+    names = (["reduce", "B gather+bar", "B rows", "A gather+bar", "A end bar", "B tma wait", "A tma wait", "A rows", "a tma", "a gb", "b wait xs", "b corr", "c gather", "c W", "c tail", "-"]
              if variant >= 3 else ["tma_wait", "S1", "reduce_wait", "S2_poll", "S2_compute", "S3_poll", "S3"])
     print(f"variant {variant}: {ms:.2f} ms, {1e3 * ms / nst:.2f} us/strip; cycles/strip (mean over CTAs | min | max):")
     for i, nm in enumerate(names):
