@@ -125,14 +125,26 @@ extern "C" int hp_precond_setup(hp_solver* s, int P, int K, int m_lo, int m_hi, 
 // developer hook: per-phase cycle counters of the sweep kernel.  on=1 allocates/zeroes, read copies [G][8] to host
 extern "C" int hp_debug_phases(hp_solver* s, int on, long long* out_host) {
     if (!s || !s->packets) return 1;
-    size_t sz = sizeof(long long) * (16 + 64 * 4) * s->lay.G;
+    size_t sz = sizeof(long long) * ((16 + 64 * 16) * s->lay.G + 2 * 64 * 32);
     if (on && !s->dbg) { HP_CUDA(cudaMalloc(&s->dbg, sz)); HP_CUDA(cudaMemset(s->dbg, 0, sz)); }
     if (out_host && s->dbg) HP_CUDA(cudaMemcpy(out_host, s->dbg, sz, cudaMemcpyDeviceToHost));
     if (!on && s->dbg) { cudaFree(s->dbg); s->dbg = nullptr; }
     return 0;
 }
-// 0 = automatic, 1 = force the direct (no shared-memory staging) sweep kernel
+// sweep kernel: 0 = automatic; classic layout: 1 direct, 2 TMA staged, 3 pipelined; cluster layout: 4
 extern "C" int hp_set_sweep_variant(hp_solver* s, int v) { if (!s) return 1; s->sweep_variant = v; return 0; }
+// generator layout chosen by the next hp_precond_setup: 0 = automatic, 1 = classic (G = P*K CTAs, N by rows),
+// 2 = cluster (a leaf is a thread-block cluster, N by separator columns)
+extern "C" int hp_set_layout_mode(hp_solver* s, int mode) {
+    if (!s || mode < 0 || mode > 2) { hp_set_error("hp_set_layout_mode: mode must be 0, 1 or 2"); return 1; }
+    s->layout_mode = mode;
+    return 0;
+}
+extern "C" int hp_strip_layout_ex(hp_solver* s, int* colN, int* NCB, int* NRQ, int* NXG) {
+    if (!s || !s->packets) { hp_set_error("hp_strip_layout_ex: preconditioner not set up"); return 1; }
+    if (colN) *colN = s->lay.colN; if (NCB) *NCB = s->lay.NCB; if (NRQ) *NRQ = s->lay.NRQ; if (NXG) *NXG = s->lay.NXG;
+    return 0;
+}
 extern "C" int64_t hp_precond_bytes(hp_solver* s) { return s ? s->bytes : 0; }
 extern "C" double hp_precond_setup_ms(hp_solver* s) { return s ? s->setup_ms : 0.0; }
 

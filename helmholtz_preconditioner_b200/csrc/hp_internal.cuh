@@ -39,6 +39,10 @@ struct HpLayout {
     int NS = 0, NSP = 0, NR = 0; // separator unknowns b*(P-1), padded row length, rows of N per CTA
     size_t PK = 0;               // complex numbers per packet
     size_t offG = 0, offN = 0;   // offsets of Gp and Np inside a packet
+    // cluster layout (csrc/hp_sweep4.cu): a leaf is one thread-block cluster of K CTAs, N is distributed by the columns
+    // of the leaf's right separator: Np [b][NRQ] = N[rows NRQ*k .. NRQ*(k+1)-1][columns of separator l], column major
+    int colN = 0;
+    int NCB = 0, NRQ = 0, NXG = 0;   // ceil(b/K) separator right-hand sides, ceil(NS/K) rows of x, ceil(3b/K) gathered entries per CTA
 };
 
 struct hp_solver {
@@ -58,7 +62,7 @@ struct hp_solver {
     int *leaf_start = nullptr, *leaf_q = nullptr, *sep = nullptr;   // device copies
     cplx* packets = nullptr;
     cplx* mleaf = nullptr;        // transfer matrices of the pipelined sweep: [strip][dir][leaf][2b][2b]
-    cplx* qmat = nullptr;         // one-hop recurrence matrices Q = N Mrho: [strip][dir][G][NR][NSP]
+    cplx* rsep = nullptr;         // cluster kernel: separator recurrence rows R: [strip][dir][P-1][b][3b]
     int64_t bytes = 0;
     double setup_ms = 0.0;
     // front block: Thomas factors of the b tridiagonal diagonal blocks (reference H_F)
@@ -67,7 +71,8 @@ struct hp_solver {
     // sweep scratch
     cplx* xch = nullptr;          // exchange ring of the sweep kernel (csrc/hp_sweep.cu)
     long long* dbg = nullptr;     // optional per-phase cycle counters of the sweep kernel [G][8]
-    int sweep_variant = 0;        // 0 = automatic (TMA double buffering when two packets fit in shared memory), 1 = direct
+    int sweep_variant = 0;        // 0 = automatic; classic layout: 1 direct, 2 TMA staged, 3 pipelined; cluster layout: 4
+    int layout_mode = 0;          // 0 = automatic (cluster layout when a partition exists), 1 = classic, 2 = cluster
     unsigned int* bar = nullptr;
     int* status = nullptr;        // device flag: non-zero when a pivot vanished during setup
     // optional CUDA-event timing of the sweep launches (hp_profile_enable / hp_profile_read)

@@ -5,6 +5,7 @@
 // Strips are independent; they are processed in batches of LB strips so that the scratch (the Schur
 // chains of every block row) stays bounded.
 #include "hp_internal.cuh"
+#include "hp_sweep4.h"
 
 #include <algorithm>
 
@@ -109,17 +110,59 @@ __global__ void __launch_bounds__(64) hp_sep_diaginv_kernel(HpSetupArgs a) {
     if (hp_sep_diag_inverse(a.Njj + o, a.FX + o, a.BX + o, a.Sd + o, a.c.b)) atomicOr(a.status, 4);
 }
 
-// thread -> (strip, separator, component): one row of N, written into the packet of the CTA that owns it
-__global__ void __launch_bounds__(128) hp_sep_rows_kernel(HpSetupArgs a) {
+// thread -> (strip, separator, component): one row of N (= column, N is symmetric).  Classic layout: written as a row
+// into the packet of the CTA that owns it.  Cluster layout: column (j, kap) belongs to cluster j, rows distributed over
+// its CTAs, Np[kap][NRQ] column major.
+__global__ void __launch_bounds__(128) hp_sep_rows_kernel(HpSetupArgs a, cplx* rowbuf) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int ns = a.lay.P - 1, b = a.c.b, bb = b * b;
     if (t >= a.nb * ns * b) return;
     int kap = t % b, j = (t / b) % ns, lb = t / (b * ns);
     int row = j * b + kap;
-    cplx* pk = hp_packet(a, lb, row / a.lay.NR);
-    cplx* nrow = pk + a.lay.offN + (size_t)(row % a.lay.NR) * a.lay.NSP;
     size_t o = (size_t)lb * ns * bb;
-    hp_sep_row(nrow, a.Njj + o, a.PF + o, a.PB + o, ns, j, kap, b);
+    if (!a.lay.colN) {
+        cplx* pk = hp_packet(a, lb, row / a.lay.NR);
+        cplx* nrow = pk + a.lay.offN + (size_t)(row % a.lay.NR) * a.lay.NSP;
+        hp_sep_row(nrow, a.Njj + o, a.PF + o, a.PB + o, ns, j, kap, b);
+    } else {
+        cplx* nrow = rowbuf + (size_t)t * a.lay.NSP;
+        hp_sep_row(nrow, a.Njj + o, a.PF + o, a.PB + o, ns, j, kap, b);
+        const int NRQ = a.lay.NRQ;
+        for (int i = 0; i < a.lay.NS; ++i) {
+            cplx* pk = hp_packet(a, lb, j * a.lay.K + i / NRQ);
+            pk[a.lay.offN + (size_t)kap * NRQ + (i % NRQ)] = nrow[i];
+        }
+    }
+}
+
+// Separator recurrence rows of the cluster sweep kernel (csrc/hp_sweep4.cu).  With x3 = [x_{j-1}; x_j; x_{j+1}] of the
+// previous strip of the sweep, rho_j(t) = rho_b(t) - R_j(t) x3(t-1),
+//   R_j[i][0..b)   = M_j[b+i][kap]                                   (gl of leaf j from x_{j-1})
+//   R_j[i][b..2b)  = M_j[b+i][b+kap] + M_{j+1}[i][kap] + cs_j [i = kap = b-1]
+//   R_j[i][2b..3b) = M_{j+1}[i][b+kap]                               (gf of leaf j+1 from x_{j+1})
+// M_l[r][c] = mleaf_l[c*2b + r]; cs_j = coupling of the separator column between the two grid rows of the pair.
+// rsep[((m-m_lo)*2 + dir)*(P-1) + j][b][3b].  CTA -> (strip, dir, j).
+__global__ void __launch_bounds__(128) hp_rsep_kernel(const cplx* __restrict__ mleaf, HpLayout lay, const int* __restrict__ sep,
+        int m_lo, int m_hi, int b, double ih2, const cplx* __restrict__ s2t, const cplx* __restrict__ is1t,
+        cplx* __restrict__ rsep) {
+    const int ns = lay.P - 1, b2 = 2 * b, b3 = 3 * b;
+    const int j = blockIdx.x % ns, dir = (blockIdx.x / ns) & 1, mi = blockIdx.x / (2 * ns);
+    const int m = m_lo + mi, mprev = dir == 0 ? m - 1 : m + 1;
+    if (mprev < m_lo || mprev > m_hi) return;                     // stays zero (first strip of a sweep: not used)
+    const cplx* Mj = mleaf + ((size_t)(mi * 2 + dir) * lay.P + j) * b2 * b2;
+    const cplx* Mj1 = Mj + (size_t)b2 * b2;
+    const cplx cs = cmul(cscale(ih2, s2t[2 * (dir == 0 ? m - 1 : m) + 1]), is1t[2 * (sep[j] + 1)]);
+    cplx* out = rsep + ((size_t)(mi * 2 + dir) * ns + j) * b * b3;
+    for (int e = threadIdx.x; e < b * b3; e += blockDim.x) {
+        const int i = e / b3, c = e - i * b3, blk = c / b, kap = c - blk * b;
+        cplx v;
+        if (blk == 0) v = Mj[(size_t)kap * b2 + b + i];
+        else if (blk == 1) {
+            v = cadd(Mj[(size_t)(b + kap) * b2 + b + i], Mj1[(size_t)kap * b2 + i]);
+            if (i == b - 1 && kap == b - 1) v = cadd(v, cs);
+        } else v = Mj1[(size_t)(b + kap) * b2 + i];
+        out[e] = v;
+    }
 }
 
 // Transfer matrices of the pipelined sweep kernel (csrc/hp_sweep.cu).  The interface data of strip m is linear
@@ -160,70 +203,12 @@ __global__ void __launch_bounds__(256) hp_mleaf_kernel(const cplx* __restrict__ 
     }
 }
 
-// One-hop form of the separator recurrence (csrc/hp_sweep3.cu).  With rho(t) = rho_b(t) - Mrho(t) x(t-1), where
-// Mrho is block tridiagonal over the separators,
-//   block (j+1, j) = M_{j+1}[Gl rows, left cols]                                   (leaf j+1 lies left of separator j+1)
-//   block (j,   j) = M_j[Gl rows, right cols] + M_{j+1}[Gf rows, left cols] + cs_j e_b e_b^T
-//   block (j-1, j) = M_j[Gf rows, right cols]
-// (cs_j = coupling of the separator column between the two grid rows of the pair), the separator solution obeys
-//   x(t) = N rho_b(t) - Q(t) x(t-1),   Q = N Mrho   dense [(P-1)b]^2, rows distributed over the CTAs like N:
-//   qmat[((m-m_lo)*2 + dir)*G + g][NR][NSP].      CTA -> (strip, dir, g); threads over the columns of Q.
-__global__ void __launch_bounds__(256) hp_q_kernel(const cplx* __restrict__ packets, const cplx* __restrict__ mleaf, HpLayout lay,
-        const int* __restrict__ sep, int m_lo, int m_hi, int b, double ih2, const cplx* __restrict__ s2t,
-        const cplx* __restrict__ is1t, cplx* __restrict__ qmat) {
-    extern __shared__ double2 sm[];
-    const int G = lay.G, P = lay.P, NS = lay.NS, NSP = lay.NSP, NR = lay.NR, b2 = 2 * b, ns = P - 1;
-    const int g = blockIdx.x % G, dir = (blockIdx.x / G) & 1, mi = blockIdx.x / (2 * G);
-    const int m = m_lo + mi, mprev = dir == 0 ? m - 1 : m + 1;
-    if (mprev < m_lo || mprev > m_hi) return;
-    const int row0 = g * NR, nrows = max(0, min(NR, NS - row0));
-    if (nrows == 0) return;
-    const cplx* Np = packets + ((size_t)mi * G + g) * lay.PK + lay.offN;
-    cplx* Ns = sm;                                    // [NR][NS]
-    for (int e = threadIdx.x; e < nrows * NS; e += blockDim.x) Ns[e] = Np[(size_t)(e / NS) * NSP + (e % NS)];
-    __syncthreads();
-    const cplx* ML = mleaf + (size_t)(mi * 2 + dir) * P * b2 * b2;       // M_l(m, dir), stored transposed [col][row]
-    const cplx rf = cscale(ih2, s2t[2 * (dir == 0 ? m - 1 : m) + 1]);
-    cplx* out = qmat + ((size_t)(mi * 2 + dir) * G + g) * NR * NSP;
-    for (int col = threadIdx.x; col < NS; col += blockDim.x) {
-        const int j = col / b, kap = col - j * b;
-        const cplx* Mj = ML + (size_t)j * b2 * b2;                        // leaf j   (left of separator j)
-        const cplx* Mj1 = ML + (size_t)(j + 1) * b2 * b2;                 // leaf j+1 (right of separator j)
-        const cplx cs = cmul(rf, is1t[2 * (sep[j] + 1)]);
-        for (int r0 = 0; r0 < nrows; r0 += 4) {
-            cplx acc[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = cmake(0.0, 0.0);
-            for (int kp = 0; kp < b; ++kp) {
-                // Mrho[(jp,kp)][(j,kap)] for jp = j-1, j, j+1 ; M_l[r][c] = stored[c*2b + r]
-                cplx m_lo_blk = j > 0 ? Mj[(size_t)(b + kap) * b2 + kp] : cmake(0.0, 0.0);                   // (j-1, j): M_j[kp][b+kap]
-                cplx m_di_blk = cadd(Mj[(size_t)(b + kap) * b2 + b + kp], Mj1[(size_t)kap * b2 + kp]);       // (j, j)
-                if (kp == b - 1 && kap == b - 1) m_di_blk = cadd(m_di_blk, cs);
-                cplx m_hi_blk = j + 1 < ns ? Mj1[(size_t)kap * b2 + b + kp] : cmake(0.0, 0.0);               // (j+1, j): M_{j+1}[b+kp][kap]
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (r0 + i < nrows) {
-                        const cplx* nr = Ns + (size_t)(r0 + i) * NS;
-                        cplx a_ = acc[i];
-                        if (j > 0) a_ = cfma(nr[(j - 1) * b + kp], m_lo_blk, a_);
-                        a_ = cfma(nr[j * b + kp], m_di_blk, a_);
-                        if (j + 1 < ns) a_ = cfma(nr[(j + 1) * b + kp], m_hi_blk, a_);
-                        acc[i] = a_;
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (r0 + i < nrows) out[(size_t)(r0 + i) * NSP + col] = acc[i];
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------
 // partition
 // ------------------------------------------------------------------------------------------------------
-static void hp_fill_layout(HpLayout& L, int n, int b, int P, int K) {
+static void hp_fill_layout(HpLayout& L, int n, int b, int P, int K, int colN) {
     int inner = n - (P - 1);
+    L = HpLayout();
     L.P = P; L.K = K; L.G = P * K;
     int qmax = (inner + P - 1) / P;
     L.QP = qmax | 1;                       // row strides are odd numbers of 16-byte entries: a quarter warp that
@@ -233,17 +218,46 @@ static void hp_fill_layout(HpLayout& L, int n, int b, int P, int K) {
     L.NR = L.NS > 0 ? (L.NS + L.G - 1) / L.G : 0;
     L.offG = (size_t)L.CW * L.QP;
     L.offN = L.offG + (size_t)2 * b * L.CW;
-    L.PK = L.offN + (size_t)L.NR * L.NSP;
+    L.colN = colN;
+    L.NCB = (b + K - 1) / K;
+    L.NRQ = L.NS > 0 ? (L.NS + K - 1) / K : 0;
+    L.NXG = (3 * b + K - 1) / K;
+    L.PK = L.offN + (colN ? (size_t)b * L.NRQ : (size_t)L.NR * L.NSP);
 }
 
-// Choose (P, K): the sweep streams one packet per CTA and strip, so the per-CTA packet size is the time
-// per strip; among the candidates that fit in memory take the smallest packet.
+// Choose (P, K): the sweep streams one packet per CTA and strip, so the per-CTA packet size is the time per strip;
+// among the candidates that fit in memory take the smallest packet.
+//   cluster layout (csrc/hp_sweep4.cu): a leaf is a cluster of K <= 4 CTAs, all P clusters must be co-resident;
+//   classic layout (csrc/hp_sweep.cu, hp_sweep2.cu): G = P*K <= #SMs.
+// layout_mode: 0 automatic (cluster when a partition exists), 1 classic, 2 cluster.
 static int hp_choose_layout(hp_solver* s, int nstrips, int P_req, int K_req, HpLayout& best) {
     const int n = s->n, b = s->b, sms = s->num_sms;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     double budget = 0.80 * (double)free_b;
     bool found = false;
+    if (s->layout_mode != 1) {
+        for (int K = 1; K <= 8; ++K) {
+            if (K_req > 0 ? K != K_req : (K != 1 && K != 2 && K != 4)) continue;
+            int Pmin = P_req > 0 ? P_req : 1, Pmax = P_req > 0 ? P_req : std::min(std::min(sms / K, 32 * HP4_PL + 1), (n + 1) / 2);
+            for (int P = Pmax; P >= Pmin; --P) {
+                int inner = n - (P - 1);
+                if (inner < P || inner / P < K) continue;
+                HpLayout L;
+                hp_fill_layout(L, n, b, P, K, 1);
+                if (found && L.PK >= best.PK) continue;
+                double bytes = (double)nstrips * (L.G * L.PK + (size_t)2 * (P - 1) * b * 3 * b) * sizeof(cplx);
+                if (bytes > budget) continue;
+                if (hp_sweep4_max_clusters(L, b) < P) continue;      // shared-memory plan + co-residency of all clusters
+                best = L; found = true;
+            }
+        }
+        if (found) return 0;
+        if (s->layout_mode == 2) {
+            hp_set_error("hp_precond_setup: no cluster partition of n=%d, b=%d (P=%d, K=%d requested) fits", n, b, P_req, K_req);
+            return 1;
+        }
+    }
     int Pmin = P_req > 0 ? P_req : 1, Pmax = P_req > 0 ? P_req : std::min(sms, (n + 1) / 2);
     for (int P = Pmin; P <= Pmax; ++P) {
         int inner = n - (P - 1);
@@ -252,7 +266,7 @@ static int hp_choose_layout(hp_solver* s, int nstrips, int P_req, int K_req, HpL
         int K = K_req > 0 ? K_req : std::min(sms / P, qmin);
         if (K < 1 || K > qmin || P * K > sms) continue;
         HpLayout L;
-        hp_fill_layout(L, n, b, P, K);
+        hp_fill_layout(L, n, b, P, K, 0);
         if (L.QP > 1024) continue;
         double bytes = (double)nstrips * L.G * L.PK * sizeof(cplx);
         if (bytes > budget) continue;
@@ -270,7 +284,7 @@ static int hp_choose_layout(hp_solver* s, int nstrips, int P_req, int K_req, HpL
 void hp_free_strips(hp_solver* s) {
     cudaFree(s->packets); s->packets = nullptr;
     cudaFree(s->mleaf); s->mleaf = nullptr;
-    cudaFree(s->qmat); s->qmat = nullptr;
+    cudaFree(s->rsep); s->rsep = nullptr;
     cudaFree(s->leaf_start); s->leaf_start = nullptr;
     cudaFree(s->leaf_q); s->leaf_q = nullptr;
     cudaFree(s->sep); s->sep = nullptr;
@@ -308,7 +322,9 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     size_t pbytes = (size_t)nstrips * L.G * L.PK * sizeof(cplx);
     HP_CUDA(cudaMalloc(&s->packets, pbytes));
     HP_CUDA(cudaMemsetAsync(s->packets, 0, pbytes, st));
-    HP_CUDA(cudaMalloc(&s->xch, sizeof(cplx) * 4 * ((size_t)n + (size_t)L.G * 2 * b + (size_t)L.P * 2 * b + L.NSP + L.P)));
+    size_t xch_classic = (size_t)n + (size_t)L.G * 2 * b + (size_t)L.P * 2 * b + L.NSP + L.P;
+    size_t xch_cluster = (size_t)L.G * b + (size_t)std::max(L.NS, 1) * (L.P | 1);
+    HP_CUDA(cudaMalloc(&s->xch, sizeof(cplx) * 4 * std::max(xch_classic, xch_cluster)));
     HP_CUDA(cudaMalloc(&s->bar, sizeof(unsigned int) * (4 + L.P)));
     HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int) * (4 + L.P), st));
     HP_CUDA(cudaMemsetAsync(s->status, 0, sizeof(int), st));
@@ -316,7 +332,8 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     s->bytes = (int64_t)pbytes;
 
     // batch size from the scratch footprint
-    size_t per_strip = ((size_t)n * bb * 2 + (size_t)n * b + (size_t)P * bb + (size_t)9 * std::max(ns, 1) * bb) * sizeof(cplx);
+    size_t per_strip = ((size_t)n * bb * 2 + (size_t)n * b + (size_t)P * bb + (size_t)9 * std::max(ns, 1) * bb +
+                        (L.colN ? (size_t)L.NS * L.NSP : 0)) * sizeof(cplx);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     size_t cap = std::min<size_t>((size_t)(0.5 * (double)free_b), (size_t)12 << 30);
@@ -325,6 +342,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     a.c = hp_ctx(s); a.lay = L; a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
     a.m_lo = m_lo; a.packets = s->packets; a.status = s->status;
     cplx* scratch = nullptr;
+    cplx* rowbuf = nullptr;
     HP_CUDA(cudaMalloc(&scratch, per_strip * LB));
     {
         cplx* p = scratch;
@@ -335,6 +353,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
         size_t sz = (size_t)LB * std::max(ns, 1) * bb;
         a.Sd = p; p += sz; a.So = p; p += sz; a.FX = p; p += sz; a.FXi = p; p += sz; a.PF = p; p += sz;
         a.BX = p; p += sz; a.BXi = p; p += sz; a.PB = p; p += sz; a.Njj = p; p += sz;
+        rowbuf = p;
     }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -356,11 +375,11 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
             hp_count_launch(); hp_sep_chain_kernel<<<(a.nb * 2 + 31) / 32, 32, 0, st>>>(a);
             hp_count_launch(); hp_sep_diaginv_kernel<<<(t4 + 63) / 64, 64, 0, st>>>(a);
             int t7 = a.nb * ns * b;
-            hp_count_launch(); hp_sep_rows_kernel<<<(t7 + 127) / 128, 128, 0, st>>>(a);
+            hp_count_launch(); hp_sep_rows_kernel<<<(t7 + 127) / 128, 128, 0, st>>>(a, rowbuf);
         }
         HP_CUDA(cudaGetLastError());
     }
-    {   // transfer matrices of the pipelined sweep
+    {   // transfer matrices of the pipelined sweeps
         size_t mbytes = (size_t)nstrips * 2 * P * 4 * bb * sizeof(cplx);
         HP_CUDA(cudaMalloc(&s->mleaf, mbytes));
         HP_CUDA(cudaMemsetAsync(s->mleaf, 0, mbytes, st));
@@ -369,20 +388,22 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
         hp_count_launch(); hp_mleaf_kernel<<<nstrips * 2 * P, 256, smem, st>>>(s->packets, L, s->leaf_start, s->leaf_q, m_lo, m_hi, b,
                                                                             1.0 / (s->pml.h * s->pml.h), s->s2t, s->is1t, s->mleaf);
         HP_CUDA(cudaGetLastError());
-        s->bytes += (int64_t)mbytes;
-        // one-hop recurrence matrices Q = N Mrho (skipped when memory is short: the sweep then uses the two-hop kernel)
-        size_t qbytes = (size_t)nstrips * 2 * L.G * L.NR * L.NSP * sizeof(cplx);
-        size_t free_q = 0, total_q = 0;
-        cudaMemGetInfo(&free_q, &total_q);
-        if (L.NS > 0 && qbytes + ((size_t)8 << 30) < free_q) {
-            HP_CUDA(cudaMalloc(&s->qmat, qbytes));
-            HP_CUDA(cudaMemsetAsync(s->qmat, 0, qbytes, st));
-            size_t qsm = sizeof(cplx) * (size_t)L.NR * L.NS;
-            if (qsm > 48 * 1024) HP_CUDA(cudaFuncSetAttribute(hp_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsm));
-            hp_count_launch(); hp_q_kernel<<<nstrips * 2 * L.G, 256, qsm, st>>>(s->packets, s->mleaf, L, s->sep, m_lo, m_hi, b,
-                                                                             1.0 / (s->pml.h * s->pml.h), s->s2t, s->is1t, s->qmat);
-            HP_CUDA(cudaGetLastError());
-            s->bytes += (int64_t)qbytes;
+        if (L.colN) {
+            // cluster kernel: the separator recurrence rows replace the per-leaf transfer matrices
+            if (ns > 0) {
+                size_t rbytes = (size_t)nstrips * 2 * ns * b * 3 * b * sizeof(cplx);
+                HP_CUDA(cudaMalloc(&s->rsep, rbytes));
+                HP_CUDA(cudaMemsetAsync(s->rsep, 0, rbytes, st));
+                hp_count_launch(); hp_rsep_kernel<<<nstrips * 2 * ns, 128, 0, st>>>(s->mleaf, L, s->sep, m_lo, m_hi, b,
+                                                                                 1.0 / (s->pml.h * s->pml.h), s->s2t, s->is1t, s->rsep);
+                HP_CUDA(cudaGetLastError());
+                s->bytes += (int64_t)rbytes;
+            }
+            HP_CUDA(cudaStreamSynchronize(st));
+            HP_CUDA(cudaFree(s->mleaf));
+            s->mleaf = nullptr;
+        } else {
+            s->bytes += (int64_t)mbytes;
         }
     }
     cudaEventRecord(e1, st);

@@ -24,6 +24,9 @@
 // L2 prefetch two strips ahead); the direct variant (packets too large for two shared-memory stages) reads
 // them from global memory behind an L2 prefetch.
 #include "hp_sweep_common.cuh"
+#include "hp_sweep4.h"
+
+#include <algorithm>
 
 #ifndef HP_SWEEP_THREADS
 #define HP_SWEEP_THREADS 256
@@ -352,8 +355,6 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
 #define HP2_OFF_COLS 256
 size_t hp_sweep2_smem(const HpLayout& L, int b);
 int hp_sweep2_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st);
-size_t hp_sweep3_smem(const HpLayout& L, int b);
-int hp_sweep3_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st);
 
 int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout, int m_from, int m_to,
                     int diag_mode, cudaStream_t st) {
@@ -369,7 +370,7 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     HpSweepArgs a;
     a.n = s->n; a.b = s->b; a.lay = s->lay;
     a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
-    a.packets = s->packets; a.mleaf = s->mleaf; a.qmat = s->qmat; a.m_lo = s->m_lo;
+    a.packets = s->packets; a.mleaf = s->mleaf; a.rsep = s->rsep; a.m_lo = s->m_lo;
     a.mode = mode; a.m_from = m_from; a.m_to = m_to; a.diag_mode = diag_mode;
     a.u = u; a.vin = vin; a.yout = yout;
     a.xch = s->xch; a.bar = s->bar;
@@ -385,22 +386,28 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     int max_smem = 0, dev = 0;
     HP_CUDA(cudaGetDevice(&dev));
     HP_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    // variants: 0 automatic; 1 direct (global loads); 2 staged, block-synchronous phases; 3 pipelined, two hand-overs per
-    // strip (csrc/hp_sweep2.cu); 4 pipelined, one hand-over per strip (csrc/hp_sweep3.cu)
-    bool pipe_ok = L.K <= 16 && L.CW <= HP2_OFF_COLS && 2 * s->b <= 64 && L.NR <= 128 && s->mleaf && hp_sweep2_smem(L, s->b) + 1024 <= (size_t)max_smem;
-    bool tma_ok = 2 * stage + small + 1024 <= (size_t)max_smem;
-    bool hop1_ok = pipe_ok && s->qmat && L.NS > 0 && hp_sweep3_smem(L, s->b) + 1024 <= (size_t)max_smem;
+    // variants: classic layout: 1 direct (global loads); 2 staged, block-synchronous phases; 3 pipelined, two hand-overs
+    // per strip (csrc/hp_sweep2.cu).  cluster layout: 4 (csrc/hp_sweep4.cu).  0 = automatic.
     int variant = s->sweep_variant;
-    if (variant == 0) variant = pipe_ok ? 3 : (tma_ok ? 2 : 1);   // measured: 3 (5.9 us/strip) < 2 (7.2) < 4 (8.0) at 4096^2
-    if (variant == 4 && !hop1_ok) variant = 3;
-    if (variant == 3 && !pipe_ok) variant = tma_ok ? 2 : 1;
-    if (variant == 2 && !tma_ok) variant = 1;
+    if (L.colN) {
+        if (variant != 0 && variant != 4) { hp_set_error("sweep: variant %d needs the classic layout (hp_set_layout_mode before setup)", variant); return 1; }
+        variant = 4;
+        a.oGP = 0; a.oXS = (size_t)L.G * s->b; a.oGR = a.oVS = 0;
+        a.slot_stride = a.oXS + (size_t)std::max(L.NS, 1) * (L.P | 1);
+    } else {
+        if (variant == 4) { hp_set_error("sweep: variant 4 needs the cluster layout (hp_set_layout_mode before setup)"); return 1; }
+        bool pipe_ok = L.K <= 16 && L.CW <= HP2_OFF_COLS && 2 * s->b <= 64 && L.NR <= 128 && s->mleaf && hp_sweep2_smem(L, s->b) + 1024 <= (size_t)max_smem;
+        bool tma_ok = 2 * stage + small + 1024 <= (size_t)max_smem;
+        if (variant == 0) variant = pipe_ok ? 3 : (tma_ok ? 2 : 1);   // measured at 4096^2: 3 (5.9 us/strip) < 2 (7.2)
+        if (variant == 3 && !pipe_ok) variant = tma_ok ? 2 : 1;
+        if (variant == 2 && !tma_ok) variant = 1;
+    }
     // the exchange ring starts all-sentinel (0xFF bytes); bar[1] = abort flag
     HP_CUDA(cudaMemsetAsync(s->xch, 0xFF, sizeof(cplx) * HP_RING * a.slot_stride, st));
     hp_count_launch();
     hp_profile_begin(s, st);
     if (variant == 4) {
-        if (hp_sweep3_launch(s, a, st)) return 2;
+        if (hp_sweep4_launch(s, a, st)) return 2;
     } else if (variant == 3) {
         if (hp_sweep2_launch(s, a, st)) return 2;
     } else {
@@ -412,7 +419,8 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
         void* args[] = {&a};
         HP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.G), dim3(HP_SWEEP_THREADS), args, smem, st));
     }
-    hp_profile_end(s, st, (int64_t)(hi - lo + 1) * ((int64_t)L.G * L.PK + 3 * (int64_t)s->n) * (int64_t)sizeof(cplx));
+    hp_profile_end(s, st, (int64_t)(hi - lo + 1) * ((int64_t)L.G * L.PK + 3 * (int64_t)s->n + (L.colN ? (int64_t)(L.P - 1) * 3 * s->b * s->b : 0)) *
+                              (int64_t)sizeof(cplx));
     return 0;
 }
 

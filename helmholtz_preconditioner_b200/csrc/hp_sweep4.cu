@@ -1,0 +1,684 @@
+// Cluster sweep kernel: the strip chain of algo2_4 (/root/reference/code.py:366-380) with ONE hand-over through L2
+// per strip.
+//
+// A leaf of the x1 partition is a thread-block cluster of K CTAs (K = cluster size <= 4); everything the CTAs of a
+// leaf exchange (the leaf's input v, the partial interface data, the separator right-hand side, the gathered
+// separator solution) goes through distributed shared memory with st.async + mbarrier complete_tx, and only the
+// separator solution x crosses between clusters, through self-validating words in L2 (csrc/hp_sweep_common.cuh).
+//
+// Cluster l owns the separator column on its right (separator l) and the 12 = b columns of N = S^-1 that belong to
+// it, distributed by rows over its CTAs.  With x3 = [x_{l-1}; x_l; x_{l+1}](t-1) the separator solution of the
+// previous strip around the leaf, the right-hand side of separator l is (hp_rsep_kernel builds R from the leaf
+// transfer matrices M = Gc(t) coef Gc(t-1)^T)
+//     rho_l(t) = rho_b(t) - R_l(t) x3(t-1),      rho_b(t) = e_b vsb(t) - glb_l(t) - gfb_{l+1}(t)
+// where glb/gfb = Gc(t) vb(t) use only the part vb(t) of the strip input that does not depend on x(t-1).
+//
+//   critical group (warps 0-3)                                   off-path group (warps 4-11)
+//   A  wait x3(t-1)                             [DSMEM]          a  gb(t) = Gc(t) vb(t): gl part -> owner CTA [DSMEM],
+//   B  rho_l(t) own entries -> all CTAs of l    [DSMEM]             gf part -> cluster l-1                    [L2]
+//   C  own rows of N[:, sep l] rho_l(t) -> XP   [L2]             b  wait x3(t-1): v(t) = vb(t) + coef Gc(t-1)^T x3
+//   D  gather: x3(t)[own entries] = sum over the separators         -> field row, v(t) -> all CTAs of l       [DSMEM]
+//      of XP -> all CTAs of l                   [DSMEM]          c  y0(t) = W(t) v_leaf(t) (W streamed in row chunks),
+//                                                                   vb(t+1)
+// The cycle x(t-1) -> x(t) is: 3b-term dot products, one DSMEM hop, b-term dot products, ONE L2 hand-over, a sum over
+// the P-1 separators, one DSMEM hop.  Everything that touches W and Gc hangs off it with a slack of one strip.
+// Generators are staged by TMA (cp.async.bulk) in shared-memory rings: W row chunks (S slots), Gc (3 strips: the
+// current one and the previous one are both live), N columns and R rows (2 strips each).
+#include "hp_sweep_common.cuh"
+#include "hp_sweep4.h"
+
+#include <stdlib.h>
+
+#define HP4_CRIT 96          // critical group: warps 0-2
+#define HP4_PROD 32          // warp 3: issues every TMA copy (its lane 0), driven by the empty barriers of the rings
+#define HP4_OFF 256          // off-path group: warps 4-11
+#define HP4_THREADS (HP4_CRIT + HP4_PROD + HP4_OFF)
+#define HP4_CW (HP4_CRIT / 32)
+
+__device__ __forceinline__ void bar_crit4() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+__device__ __forceinline__ void bar_off4() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned int mapa_u32(unsigned int local_addr, unsigned int rank) {
+    unsigned int r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+// one complex number into the shared memory of a CTA of the cluster; the 16 bytes are counted on that CTA's mbarrier
+__device__ __forceinline__ void st_async_cplx(unsigned int remote_addr, cplx v, unsigned int remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
+                 ::"r"(remote_addr), "l"(__double_as_longlong(v.x)), "l"(__double_as_longlong(v.y)), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cluster(unsigned long long* bar, unsigned int parity) {
+    unsigned int ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a runaway wait (a bug) marks the CTA dead, all later waits fall through and the kernel terminates
+__device__ __forceinline__ void mbar_wait4(unsigned long long* bar, unsigned int parity, unsigned int* abort_flag,
+                                           volatile unsigned int* dead) {
+    unsigned int spins = 0;
+    while (!mbar_try_cluster(bar, parity)) {
+        if (*dead) break;
+        if (++spins > (1u << 20)) { atomicExch(abort_flag, 1u); *dead = 1u; break; }
+        if ((spins & 0x3FF) == 0 && *((volatile unsigned int*)abort_flag)) { *dead = 1u; break; }
+    }
+}
+__device__ __forceinline__ void mbar_arrive_local(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ring_fill4(unsigned char* dst, const cplx* src, unsigned int bytes, unsigned long long* bar) {
+    mbar_expect_tx(bar, bytes);
+    for (unsigned int o = 0; o < bytes; o += HP_BULK_CHUNK)
+        bulk_g2s(dst + o, (const char*)src + o, min(HP_BULK_CHUNK, bytes - o), bar);
+}
+
+// MODE: 0 forward, 1 backward (reference diagonal), 2 backward (paper diagonal), 3 single strip apply
+template <int MODE, bool DBG>
+__global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a, Hp4Plan pl) {
+    constexpr int a_mode = MODE == 0 ? 0 : (MODE == 3 ? 2 : 1);
+    constexpr int a_diag = MODE == 2 ? 1 : 0;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int b = a.b, b2 = 2 * a.b, b3 = 3 * a.b, n = a.n, K = a.lay.K, P = a.lay.P, QP = a.lay.QP, CW = a.lay.CW;
+    const int NS = a.lay.NS, NRQ = a.lay.NRQ, NXG = a.lay.NXG;
+    const int PP = P | 1;                          // partial solutions are stored entry-major [NS][PP]: the lanes of a warp poll
+                                                   // the P-1 contributions to one entry with one coalesced load
+    const int g = blockIdx.x, l = g / K, k = g - l * K;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int q = a.leaf_q[l], ls = a.leaf_start[l];
+    const int lc0 = (q * k) / K, lc1 = (q * (k + 1)) / K, ncols = lc1 - lc0, c0 = ls + lc0;
+    unsigned int* abort_flag = a.bar + 1;
+    const int step = a_mode == 1 ? -1 : 1;
+    const int nsteps = a_mode == 2 ? 1 : (a_mode == 0 ? a.m_to - a.m_from + 1 : a.m_from - a.m_to + 1);
+    const int dir = a_mode == 1 ? 1 : 0;
+    const double sg = a_diag == 0 ? 1.0 : -1.0;
+    const bool any_sep = NS > 0;
+    const bool has_sep = l < P - 1;                // this cluster owns separator l
+    const int nrq_own = has_sep ? max(0, min(NRQ, NS - NRQ * k)) : 0;    // rows of x this CTA forms
+    const int nxg_own = any_sep ? max(0, min(NXG, b3 - NXG * k)) : 0;    // entries of x3 this CTA gathers
+    const int S = pl.S, RC = pl.RC, NCH = pl.NCH;
+
+    // ---- shared memory carve-up (must match hp_sweep4_plan; identical in every CTA: DSMEM addresses are mapped)
+    unsigned char* ringW = smem_raw;
+    unsigned char* ringG = ringW + (size_t)S * pl.w_st;
+    unsigned char* ringN = ringG + 3 * pl.g_st;
+    unsigned char* ringR = ringN + 2 * pl.n_st;
+    cplx* vb = reinterpret_cast<cplx*>(ringR + 2 * pl.r_st);     // [CW]        x-independent part of the strip input
+    cplx* v_leaf = vb + CW;                                      // [2][QP]     input of the leaf            (DSMEM target)
+    cplx* y0s = v_leaf + 2 * (size_t)QP;                         // [CW]        leaf product on the own columns
+    cplx* x3 = y0s + CW;                                         // [2][3b]     x around the leaf            (DSMEM target)
+    cplx* glp = x3 + 2 * (size_t)b3;                             // [2][K][b]   partial gl of the K parts    (DSMEM target)
+    cplx* rho_s = glp + 2 * (size_t)K * b;                       // [b]         rho of separator l
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(rho_s + b);
+    unsigned long long* barW = mbar;                 // [S]
+    unsigned long long* barG = barW + S;             // [3]
+    unsigned long long* barN = barG + 3;             // [2]
+    unsigned long long* barR = barN + 2;             // [2]
+    unsigned long long* barX = barR + 2;             // [2]  x3
+    unsigned long long* barGL = barX + 2;            // [2]  glp
+    unsigned long long* barV = barGL + 2;            // [2]  v_leaf
+    unsigned long long* eW = barV + 2;               // [S]  "slot free" barriers: one arrival per consuming warp
+    unsigned long long* eG = eW + S;                 // [3]
+    unsigned long long* eN = eG + 3;                 // [2]
+    unsigned long long* eR = eN + 2;                 // [2]
+    volatile unsigned int* dead = reinterpret_cast<volatile unsigned int*>(eR + 2);
+
+    const cplx* pk_base = a.packets + (size_t)g * a.lay.PK;
+    const size_t strip_stride = (size_t)a.lay.G * a.lay.PK;
+    const int m0 = a.m_from;
+    const unsigned int x_bytes = (unsigned int)(b3 * sizeof(cplx)), gl_bytes = (unsigned int)((size_t)K * b * sizeof(cplx)),
+                       v_bytes = (unsigned int)(q * sizeof(cplx));
+
+    if (tid == 0) {
+        for (int i = 0; i < S + 13; ++i) mbar_init(&mbar[i], 1);
+        for (int i = 0; i < S + 3; ++i) mbar_init(&eW[i], HP4_OFF / 32);
+        for (int i = 0; i < 4; ++i) mbar_init(&eN[i], HP4_CW);
+        *dead = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+        // the DSMEM barriers of the first two strips are armed before any CTA of the cluster can send
+        for (int p = 0; p < 2; ++p) {
+            if (any_sep) mbar_expect_tx(&barX[p], x_bytes);
+            if (has_sep) mbar_expect_tx(&barGL[p], gl_bytes);
+            mbar_expect_tx(&barV[p], v_bytes);
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();
+
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
+#define HP_TICK(i) do { if (DBG && lane == 0 && (tid == 0 || tid == HP4_CRIT + HP4_PROD)) { long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
+    // timeline window: globaltimer stamps of strips 512..575, 8 per group, [G][64][16] behind the [G][16] phase sums
+#define HP_STAMP4(kk) do { if (DBG && (tid == 0 || tid == HP4_CRIT + HP4_PROD) && it >= 512 && it < 576) { unsigned long long t_; \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+        a.dbg[(size_t)a.lay.G * 16 + ((size_t)g * 64 + (it - 512)) * 16 + (tid == 0 ? 0 : 8) + (kk)] = (long long)t_; } } while (0)
+
+    if (tid < HP4_CRIT) {
+        // =====================================================================================================
+        // critical group.  Every CTA of the cluster forms all b entries of rho_l (no hop between B and C):
+        // thread -> (entry e = ctid/8 + 12*pass, part = ctid%8)
+        // =====================================================================================================
+        const int ctid = tid, cw = ctid >> 5, part = ctid & 7, e_lo = ctid >> 3;
+        constexpr int EPP = HP4_CRIT / 8;                       // entries per pass
+        constexpr int NPASS = (HP_BMAX + EPP - 1) / EPP;
+        // the thread that forms entry b-1 of rho_l keeps the separator column (every CTA of the cluster follows it, the
+        // first one writes the field)
+        const bool is_sep = has_sep && part == 0 && e_lo == (b - 1) % EPP;
+        const int sep_pass = (b - 1) / EPP;
+        const int sep_col = has_sep ? a.sep[l] : 0;
+        const cplx cis1s = is_sep ? a.is1t[2 * (sep_col + 1)] : cmake(0.0, 0.0);
+        cplx usbase = cmake(0.0, 0.0), vsb = cmake(0.0, 0.0);
+        cplx o_usep = cmake(0.0, 0.0), o_c = cmake(0.0, 0.0), o_usbase = cmake(0.0, 0.0);   // what the output of the previous strip needs
+        if (is_sep) {
+            if (a_mode == 2) vsb = a.vin[sep_col];
+            else if (a_mode == 0) vsb = ldcg(a.u + (size_t)(m0 - 1) * n + sep_col);
+            else {
+                usbase = ldcg(a.u + (size_t)(m0 - 1) * n + sep_col);
+                vsb = usbase;
+                if (m0 < n) vsb = cfma(cscale(sg, cmul(hp_rowfac(a, m0), cis1s)), ldcg(a.u + (size_t)m0 * n + sep_col), vsb);
+            }
+        }
+        auto sep_output = [&](int m_prev, cplx ys) {          // y_s = x_l[b-1] of strip m_prev
+            if (k != 0) return;
+            if (a_mode == 2) a.yout[sep_col] = ys;
+            else if (a_mode == 0) a.u[(size_t)m_prev * n + sep_col] = cfms(o_c, ys, o_usep);
+            else a.u[(size_t)(m_prev - 1) * n + sep_col] = a_diag == 0 ? csub(o_usbase, ys) : ys;
+        };
+
+        for (int it = 0; it < nsteps; ++it) {
+            const int m = m0 + it * step, mn = m + step;
+            const bool more = it + 1 < nsteps;
+            const int par = it & 1, ph = (it >> 1) & 1;
+            cplx* slot = a.xch + (size_t)(it & (HP_RING - 1)) * a.slot_stride;
+            cplx* slot_next = a.xch + (size_t)((it + 1) & (HP_RING - 1)) * a.slot_stride;      // strip it-3: every reader is done
+            const cplx* x3p = x3 + (size_t)(par ^ 1) * b3;                                      // x3(it-1)
+            if (DBG && tid == 0) tprev = clock64();
+            HP_STAMP4(0);
+            // early loads of the separator column (x-independent)
+            cplx usep = cmake(0.0, 0.0), cs = cmake(0.0, 0.0);
+            if (is_sep) {
+                cs = cmul(hp_rowfac(a, a_mode == 1 ? mn : m), cis1s);
+                if (a_mode == 0) usep = ldcg(a.u + (size_t)m * n + sep_col);
+                else if (a_mode == 1 && more) usep = ldcg(a.u + (size_t)(mn - 1) * n + sep_col);
+            }
+            // ---- x-independent part of rho_l(it): own-cluster gl partials (DSMEM) + gf partials of leaf l+1 (L2)
+            cplx pre[NPASS];
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ++ps) pre[ps] = cmake(0.0, 0.0);
+            if (has_sep) {
+                mbar_wait4(&barGL[par], ph, abort_flag, dead);
+#pragma unroll
+                for (int ps = 0; ps < NPASS; ++ps) {
+                    const int e = e_lo + EPP * ps;
+                    if (e < b && part < K) {
+                        cplx gf = cmake(0.0, 0.0);
+                        const cplx* pg = slot + a.oGP + ((size_t)(l + 1) * K + part) * b + e;
+                        unsigned int spins = 0;
+                        while (!xtry(pg, gf)) {
+                            if (*dead) break;
+                            if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; break; }
+                            if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) { *dead = 1u; break; }
+                        }
+                        pre[ps] = cadd(glp[((size_t)par * K + part) * b + e], gf);
+                    }
+                }
+                mbar_wait4(&barR[par], ph, abort_flag, dead);
+            }
+            HP_TICK(0);
+            HP_STAMP4(1);
+            // ---- A: x3(it-1)
+            if (it > 0 && any_sep) {
+                mbar_wait4(&barX[par ^ 1], ((it - 1) >> 1) & 1, abort_flag, dead);
+                if (ctid == 0 && it + 1 < nsteps) mbar_expect_tx(&barX[par ^ 1], x_bytes);      // strip it+1
+            }
+            HP_TICK(1);
+            HP_STAMP4(2);
+            if (has_sep) {
+                // ---- B: rho_l(it) = rho_b - R x3(it-1)
+                const cplx* R = reinterpret_cast<const cplx*>(ringR + par * pl.r_st);
+#pragma unroll
+                for (int ps = 0; ps < NPASS; ++ps) {
+                    const int e = e_lo + EPP * ps;
+                    cplx tot = pre[ps];
+                    if (e < b && it > 0) {
+                        const cplx* Rr = R + (size_t)e * b3;
+                        cplx a0 = cmake(0.0, 0.0), a1 = cmake(0.0, 0.0);
+                        int c = part;
+                        for (; c + 8 < b3; c += 16) { a0 = cfma(Rr[c], x3p[c], a0); a1 = cfma(Rr[c + 8], x3p[c + 8], a1); }
+                        if (c < b3) a0 = cfma(Rr[c], x3p[c], a0);
+                        tot = cadd(tot, cadd(a0, a1));
+                    }
+                    if (EPP * ps < b) {                         // warp-uniform
+#pragma unroll
+                        for (int o = 1; o < 8; o <<= 1) {
+                            tot.x += __shfl_xor_sync(0xffffffffu, tot.x, o);
+                            tot.y += __shfl_xor_sync(0xffffffffu, tot.y, o);
+                        }
+                        if (e < b && part == 0) {
+                            cplx rho = cneg(tot);
+                            if (is_sep && ps == sep_pass) rho = cadd(rho, vsb);
+                            rho_s[e] = rho;
+                        }
+                    }
+                }
+            }
+            if (is_sep) {
+                if (it > 0) sep_output(m - step, x3p[b2 - 1]);
+                o_usep = usep; o_c = cs; o_usbase = usbase;
+                // x-independent part of the next strip's separator input
+                if (a_mode == 0) vsb = usep;
+                else if (a_mode == 1) { vsb = a_diag == 0 ? cfma(cs, usbase, usep) : usep; usbase = usep; }
+            }
+            if (has_sep) {
+                bar_crit4();
+                HP_TICK(2);
+                HP_STAMP4(3);
+                // ---- C: own rows of x(it) restricted to the columns of separator l
+                if (nrq_own > 0) mbar_wait4(&barN[par], ph, abort_flag, dead);
+                const cplx* Np = reinterpret_cast<const cplx*>(ringN + par * pl.n_st);
+                for (int r = ctid; r < nrq_own; r += HP4_CRIT) {
+                    cplx a0 = cmake(0.0, 0.0), a1 = cmake(0.0, 0.0), a2 = cmake(0.0, 0.0), a3 = cmake(0.0, 0.0);
+                    int c = 0;
+                    for (; c + 3 < b; c += 4) {
+                        a0 = cfma(Np[(size_t)c * NRQ + r], rho_s[c], a0);
+                        a1 = cfma(Np[(size_t)(c + 1) * NRQ + r], rho_s[c + 1], a1);
+                        a2 = cfma(Np[(size_t)(c + 2) * NRQ + r], rho_s[c + 2], a2);
+                        a3 = cfma(Np[(size_t)(c + 3) * NRQ + r], rho_s[c + 3], a3);
+                    }
+                    for (; c < b; ++c) a0 = cfma(Np[(size_t)c * NRQ + r], rho_s[c], a0);
+                    xput(slot + a.oXS + (size_t)(NRQ * k + r) * PP + l, cadd(cadd(a0, a1), cadd(a2, a3)));
+                    xarm(slot_next + a.oXS + (size_t)(NRQ * k + r) * PP + l);
+                }
+                HP_TICK(3);
+                HP_STAMP4(4);
+                // this warp is done with the N and R stages of the strip: the producer warp may refill them
+                __syncwarp();
+                if (lane == 0) { mbar_arrive_local(&eN[par]); mbar_arrive_local(&eR[par]); }
+                if (ctid == 0 && it + 2 < nsteps) mbar_expect_tx(&barGL[par], gl_bytes);
+            }
+            // ---- D: gather x3(it): own entries summed over the P-1 partial solutions, sent to every CTA of the leaf
+            if (any_sep) {
+                for (int tb = 0; tb < nxg_own; tb += HP4_CW * HP4_EW) {     // one batch when ceil(3b/K) <= 3*HP4_EW
+                    int ent[HP4_EW];
+                    cplx val[HP4_EW][HP4_PL];
+#pragma unroll
+                    for (int o = 0; o < HP4_EW; ++o) {
+                        const int tt = tb + cw + HP4_CW * o;
+                        const int e = tt < nxg_own ? (l - 1) * b + NXG * k + tt : -1;
+                        ent[o] = (e >= 0 && e < NS) ? e : -1;
+#pragma unroll
+                        for (int pp = 0; pp < HP4_PL; ++pp) val[o][pp] = cmake(0.0, 0.0);
+                    }
+                    // all loads of a round are issued back to back; the warp leaves the loop as a whole
+                    unsigned int spins = 0;
+                    for (;;) {
+                        unsigned long long lo[HP4_EW][HP4_PL], hi[HP4_EW][HP4_PL];
+#pragma unroll
+                        for (int o = 0; o < HP4_EW; ++o)
+#pragma unroll
+                            for (int pp = 0; pp < HP4_PL; ++pp) {
+                                lo[o][pp] = hi[o][pp] = 0ull;
+                                if (ent[o] >= 0 && lane + 32 * pp < P - 1) xload(slot + a.oXS + (size_t)ent[o] * PP + lane + 32 * pp, lo[o][pp], hi[o][pp]);
+                            }
+                        bool ok = true;
+#pragma unroll
+                        for (int o = 0; o < HP4_EW; ++o)
+#pragma unroll
+                            for (int pp = 0; pp < HP4_PL; ++pp) {
+                                ok = ok && xvalid(lo[o][pp], hi[o][pp]);
+                                val[o][pp] = cmake(__longlong_as_double((long long)lo[o][pp]), __longlong_as_double((long long)hi[o][pp]));
+                            }
+                        if (__all_sync(0xffffffffu, ok || *dead)) break;
+                        if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; }
+                        if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) *dead = 1u;
+                    }
+                    if (DBG && (g == 5 || g == 64) && cw == 0 && it >= 512 && it < 576) {      // per-lane arrival of the gathered words
+                        unsigned long long t_;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+                        a.dbg[(size_t)a.lay.G * 16 * 65 + ((size_t)(g == 5 ? 0 : 1) * 64 + (it - 512)) * 32 + lane] = (long long)t_;
+                    }
+                    HP_TICK(4);
+                    HP_STAMP4(5);
+                    cplx sums[HP4_EW];
+#pragma unroll
+                    for (int o = 0; o < HP4_EW; ++o) {
+                        cplx sacc = val[o][0];
+#pragma unroll
+                        for (int pp = 1; pp < HP4_PL; ++pp) sacc = cadd(sacc, val[o][pp]);
+                        sums[o] = hp_warp_sum2(sacc);
+                    }
+                    HP_STAMP4(6);
+#pragma unroll
+                    for (int o = 0; o < HP4_EW; ++o) {
+                        const int tt = tb + cw + HP4_CW * o;
+                        if (tt < nxg_own && lane < K)
+                            st_async_cplx(mapa_u32(smem_u32(x3 + (size_t)par * b3 + NXG * k + tt), lane), sums[o],
+                                          mapa_u32(smem_u32(&barX[par]), lane));
+                    }
+                }
+                HP_TICK(5);
+                HP_STAMP4(7);
+            }
+        }
+        // output of the last strip on the separator column
+        if (any_sep && nsteps > 0 && is_sep) {
+            const int itl = nsteps - 1;
+            mbar_wait4(&barX[itl & 1], (itl >> 1) & 1, abort_flag, dead);
+            sep_output(m0 + itl * step, x3[(size_t)(itl & 1) * b3 + b2 - 1]);
+        }
+        if (DBG && tid == 0)
+            for (int i = 0; i < 8; ++i) a.dbg[(size_t)g * 16 + i] = tacc[i];
+    } else if (tid < HP4_CRIT + HP4_PROD) {
+        // =====================================================================================================
+        // producer warp: lane 0 issues every TMA copy of the sweep, in the order the strips need them, as soon as the
+        // consumers have released the ring slot (item i of a ring of depth D waits for the release of item i-D)
+        // =====================================================================================================
+        if (lane == 0) {
+            const unsigned int n_bytes = (unsigned int)((size_t)b * NRQ * sizeof(cplx)), r_bytes = (unsigned int)((size_t)b * b3 * sizeof(cplx));
+            const unsigned int g_bytes = (unsigned int)((size_t)b2 * CW * sizeof(cplx)), pk_bytes = (unsigned int)(a.lay.PK * sizeof(cplx));
+            const cplx* n_base = pk_base + a.lay.offN;
+            const cplx* g_base = pk_base + a.lay.offG;
+            const size_t r_stride = (size_t)2 * (P - 1) * b * b3;
+            const cplx* r_base = has_sep ? a.rsep + ((size_t)dir * (P - 1) + l) * b * b3 : nullptr;
+            for (int it = 0; it < nsteps; ++it) {
+                const size_t so = (size_t)(m0 + it * step - a.m_lo);
+                if (it + 2 < nsteps) {                        // HBM -> L2 two strips ahead of the copies
+                    const char* src = (const char*)(pk_base + (size_t)(m0 + (it + 2) * step - a.m_lo) * strip_stride);
+                    for (unsigned int o = 0; o < pk_bytes; o += HP_BULK_CHUNK) bulk_prefetch_l2(src + o, min(HP_BULK_CHUNK, pk_bytes - o));
+                }
+                if (it >= 3) mbar_wait4(&eG[it % 3], ((it / 3) - 1) & 1, abort_flag, dead);
+                ring_fill4(ringG + (size_t)(it % 3) * pl.g_st, g_base + so * strip_stride, g_bytes, &barG[it % 3]);
+                if (has_sep) {
+                    if (it >= 2) { mbar_wait4(&eN[it & 1], ((it >> 1) - 1) & 1, abort_flag, dead); mbar_wait4(&eR[it & 1], ((it >> 1) - 1) & 1, abort_flag, dead); }
+                    if (nrq_own > 0) ring_fill4(ringN + (size_t)(it & 1) * pl.n_st, n_base + so * strip_stride, n_bytes, &barN[it & 1]);
+                    ring_fill4(ringR + (size_t)(it & 1) * pl.r_st, r_base + so * r_stride, r_bytes, &barR[it & 1]);
+                }
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const int cidx = it * NCH + ch, sl = cidx % S, r0 = ch * RC;
+                    if (cidx >= S) mbar_wait4(&eW[sl], ((cidx / S) - 1) & 1, abort_flag, dead);
+                    ring_fill4(ringW + (size_t)sl * pl.w_st, pk_base + so * strip_stride + (size_t)r0 * QP,
+                               (unsigned int)((size_t)min(RC, CW - r0) * QP * sizeof(cplx)), &barW[sl]);
+                }
+            }
+        }
+    } else {
+        // =====================================================================================================
+        // off-path group
+        // =====================================================================================================
+        const int ot = tid - HP4_CRIT - HP4_PROD, ow = ot >> 5;
+        const bool col = ot < ncols;
+        const int c = c0 + ot;
+        const cplx cis1 = col ? a.is1t[2 * (c + 1)] : cmake(0.0, 0.0);
+        // per-column state: vbr = vb(t), y0prev = y0(t-1), coefc = multiplier of the correction in v(t),
+        // ubase = (backward) original value of the row strip t-1 overwrites
+        cplx vbr = cmake(0.0, 0.0), y0prev = cmake(0.0, 0.0), coefc = cmake(0.0, 0.0), ubase = cmake(0.0, 0.0),
+             ubase_prev = cmake(0.0, 0.0);
+        if (col) {
+            if (a_mode == 2) vbr = a.vin[c];
+            else if (a_mode == 0) vbr = ldcg(a.u + (size_t)(m0 - 1) * n + c);
+            else {
+                ubase = ldcg(a.u + (size_t)(m0 - 1) * n + c);
+                vbr = ubase;
+                if (m0 < n) vbr = cfma(cscale(sg, cmul(hp_rowfac(a, m0), cis1)), ldcg(a.u + (size_t)m0 * n + c), vbr);
+            }
+            vb[ot] = vbr;
+        }
+        bar_off4();
+        // leaf product: RC/8 rows per warp, LPR lanes per row
+        const int RW = RC >> 3, LPR = 32 / RW;
+        const int wr_r = ow * RW + lane / LPR, wr_cp = lane % LPR;
+        const int gpart = ot & 7, gkap_lo = ot >> 3;            // interface data: 8 lanes per component
+
+        for (int it = 0; it <= nsteps; ++it) {
+            const int m = m0 + it * step, mn = m + step, mp = m - step;     // this, next, previous strip
+            const bool live = it < nsteps, more = it + 1 < nsteps;
+            const int par = it & 1, ph = (it >> 1) & 1;
+            cplx* slot = a.xch + (size_t)(it & (HP_RING - 1)) * a.slot_stride;
+            cplx* slot_arm = a.xch + (size_t)((it + 2) & (HP_RING - 1)) * a.slot_stride;
+            const cplx* Gp = reinterpret_cast<const cplx*>(ringG + (size_t)(it % 3) * pl.g_st);
+            const cplx* Gprev = reinterpret_cast<const cplx*>(ringG + (size_t)((it + 2) % 3) * pl.g_st);   // strip it-1
+            // early loads: the row coupling and the field value vb(t+1) is built from (written by no other thread)
+            const cplx rf_it = hp_rowfac(a, a_mode == 1 ? mn : m);
+            cplx unx = cmake(0.0, 0.0);
+            if (col && live) {
+                if (a_mode == 0) unx = ldcg(a.u + (size_t)m * n + c);
+                else if (a_mode == 1 && more) unx = ldcg(a.u + (size_t)(mn - 1) * n + c);
+            }
+            if (DBG && ot == 0) tprev = clock64();
+            HP_STAMP4(0);
+            // ---- a: gb(t) = Gc(t) vb(t): 8 lanes per component, gf -> cluster l-1 (L2), gl -> every CTA of the cluster
+            if (live) {
+                mbar_wait4(&barG[it % 3], (it / 3) & 1, abort_flag, dead);
+                HP_TICK(0);
+                HP_STAMP4(1);
+                if (any_sep) {
+                    for (int kap0 = 0; kap0 < b2; kap0 += HP4_OFF / 8) {
+                        const int kap = kap0 + gkap_lo;
+                        cplx acc = cmake(0.0, 0.0), a1 = cmake(0.0, 0.0);
+                        if (kap < b2) {
+                            const cplx* gr = Gp + (size_t)kap * CW;
+                            int cc = gpart;
+                            for (; cc + 8 < ncols; cc += 16) { acc = cfma(gr[cc], vb[cc], acc); a1 = cfma(gr[cc + 8], vb[cc + 8], a1); }
+                            if (cc < ncols) acc = cfma(gr[cc], vb[cc], acc);
+                            acc = cadd(acc, a1);
+                        }
+#pragma unroll
+                        for (int o = 1; o < 8; o <<= 1) {
+                            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                        }
+                        if (kap < b) {                         // gf part: to the cluster on the left
+                            if (l > 0 && gpart == 0) {
+                                xput(slot + a.oGP + ((size_t)l * K + k) * b + kap, acc);
+                                xarm(slot_arm + a.oGP + ((size_t)l * K + k) * b + kap);
+                            }
+                        } else if (kap < b2 && has_sep && gpart < K) {
+                            st_async_cplx(mapa_u32(smem_u32(glp + ((size_t)par * K + k) * b + (kap - b)), gpart), acc,
+                                          mapa_u32(smem_u32(&barGL[par]), gpart));
+                        }
+                    }
+                }
+            }
+            HP_TICK(1);
+            HP_STAMP4(2);
+            // ---- b: x3(t-1) arrives: finish strip t-1 on the own columns, input of strip t
+            cplx v = vbr;
+            if (it > 0) {
+                cplx corr = cmake(0.0, 0.0);
+                if (any_sep) {
+                    mbar_wait4(&barX[par ^ 1], ((it - 1) >> 1) & 1, abort_flag, dead);
+                    HP_TICK(2);
+                    HP_STAMP4(3);
+                    const cplx* xa = x3 + (size_t)(par ^ 1) * b3;              // [x_{l-1}; x_l] are its first 2b entries
+                    if (col) {
+                        cplx c1 = cmake(0.0, 0.0), c2 = cmake(0.0, 0.0), c3 = cmake(0.0, 0.0);
+                        int kap = 0;
+#pragma unroll 2
+                        for (; kap + 3 < b2; kap += 4) {
+                            corr = cfma(Gprev[(size_t)kap * CW + ot], xa[kap], corr);
+                            c1 = cfma(Gprev[(size_t)(kap + 1) * CW + ot], xa[kap + 1], c1);
+                            c2 = cfma(Gprev[(size_t)(kap + 2) * CW + ot], xa[kap + 2], c2);
+                            c3 = cfma(Gprev[(size_t)(kap + 3) * CW + ot], xa[kap + 3], c3);
+                        }
+                        for (; kap < b2; ++kap) corr = cfma(Gprev[(size_t)kap * CW + ot], xa[kap], corr);
+                        corr = cadd(cadd(corr, c1), cadd(c2, c3));
+                    }
+                }
+                if (col) v = cfma(coefc, corr, vbr);
+                // ---- c (first half): the leaf's input to every CTA of the cluster, before the field store
+                if (col && live)
+                    for (int j = 0; j < K; ++j)
+                        st_async_cplx(mapa_u32(smem_u32(v_leaf + (size_t)par * QP + lc0 + ot), j), v, mapa_u32(smem_u32(&barV[par]), j));
+                if (col) {
+                    if (a_mode == 2) a.yout[c] = csub(y0prev, corr);
+                    else if (a_mode == 0) a.u[(size_t)mp * n + c] = v;                      // row m_{t-1}: final
+                    else {
+                        cplx un = a_diag == 0 ? cadd(csub(ubase_prev, y0prev), corr) : csub(y0prev, corr);
+                        a.u[(size_t)(mp - 1) * n + c] = un;
+                    }
+                }
+            } else if (col && live) {
+                for (int j = 0; j < K; ++j)
+                    st_async_cplx(mapa_u32(smem_u32(v_leaf + (size_t)par * QP + lc0 + ot), j), v, mapa_u32(smem_u32(&barV[par]), j));
+            }
+            if (it > 0) {                                    // Gc(it-1) was last read above
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(&eG[(it + 2) % 3]);
+            }
+            if (!live) break;
+            HP_TICK(3);
+            HP_STAMP4(4);
+            // ---- c: leaf product y0(t) = W(t) v_leaf(t) (W in row chunks, LPR lanes per row), vb(t+1)
+            mbar_wait4(&barV[par], ph, abort_flag, dead);
+            HP_TICK(4);
+            HP_STAMP4(5);
+            const cplx* vl = v_leaf + (size_t)par * QP;
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int cidx = it * NCH + ch, sl = cidx % S, r0 = ch * RC;
+                mbar_wait4(&barW[sl], (cidx / S) & 1, abort_flag, dead);
+                const cplx* Wc = reinterpret_cast<const cplx*>(ringW + (size_t)sl * pl.w_st);
+                cplx acc = cmake(0.0, 0.0), a1 = cmake(0.0, 0.0), a2 = cmake(0.0, 0.0), a3 = cmake(0.0, 0.0);
+                if (r0 + wr_r < ncols) {
+                    const cplx* wr = Wc + (size_t)wr_r * QP;
+                    int cq = wr_cp;
+                    for (; cq + 3 * LPR < q; cq += 4 * LPR) {
+                        acc = cfma(wr[cq], vl[cq], acc);
+                        a1 = cfma(wr[cq + LPR], vl[cq + LPR], a1);
+                        a2 = cfma(wr[cq + 2 * LPR], vl[cq + 2 * LPR], a2);
+                        a3 = cfma(wr[cq + 3 * LPR], vl[cq + 3 * LPR], a3);
+                    }
+                    for (; cq < q; cq += LPR) acc = cfma(wr[cq], vl[cq], acc);
+                }
+                acc = cadd(cadd(acc, a1), cadd(a2, a3));
+                for (int o = LPR >> 1; o > 0; o >>= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                }
+                if (wr_cp == 0 && r0 + wr_r < ncols) y0s[r0 + wr_r] = acc;
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(&eW[sl]);   // this warp is done with the chunk
+            }
+            bar_off4();                                      // y0s complete
+            HP_TICK(5);
+            HP_STAMP4(6);
+            if (ot == 0 && it + 2 < nsteps) mbar_expect_tx(&barV[par], v_bytes);
+            if (col) {
+                cplx y0 = y0s[ot];
+                y0prev = y0;
+                if (a_mode == 0) {
+                    coefc = cmul(rf_it, cis1);                                 // A_{m+1,m}
+                    vbr = cfms(coefc, y0, unx);                                // u_{m+1} - coef y0
+                } else if (a_mode == 1) {
+                    coefc = cmul(rf_it, cis1);                                 // A_{m-1,m}
+                    vbr = a_diag == 0 ? cfma(coefc, csub(ubase, y0), unx) : cfms(coefc, y0, unx);
+                    ubase_prev = ubase;
+                    ubase = unx;
+                }
+                vb[ot] = vbr;
+            }
+            bar_off4();                                      // vb ready, y0s free for the next strip
+            HP_TICK(6);
+            HP_STAMP4(7);
+        }
+        if (DBG && ot == 0)
+            for (int i = 0; i < 8; ++i) a.dbg[(size_t)g * 16 + 8 + i] = tacc[i];
+    }
+    // no CTA leaves while a peer may still write into its shared memory
+    __syncthreads();
+    cluster_sync_all();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side: shared-memory plan, co-residency check, launch
+// ------------------------------------------------------------------------------------------------------
+static inline size_t al128(size_t x) { return (x + 127) & ~(size_t)127; }
+
+int hp_sweep4_plan(const HpLayout& L, int b, size_t max_smem, Hp4Plan& pl) {
+    if (!L.colN || L.K < 1 || L.K > 8) return 1;
+    if (L.P - 1 > 32 * HP4_PL || L.CW > HP4_OFF || b > HP_BMAX) return 1;
+    pl.g_st = al128((size_t)2 * b * L.CW * sizeof(cplx));
+    pl.n_st = al128(std::max<size_t>(1, (size_t)b * L.NRQ) * sizeof(cplx));
+    pl.r_st = al128((size_t)b * 3 * b * sizeof(cplx));
+    size_t small = sizeof(cplx) * ((size_t)L.CW + 2 * (size_t)L.QP + L.CW + 2 * (size_t)3 * b + 2 * (size_t)L.K * b + (size_t)b) +
+                   8 * (2 * 8 + 13 + 7) + 16;
+    size_t fixed = 3 * pl.g_st + 2 * pl.n_st + 2 * pl.r_st + al128(small);
+    if (fixed + 1024 >= max_smem) return 1;
+    size_t avail = max_smem - 1024 - fixed;
+    size_t row = (size_t)L.QP * sizeof(cplx);
+    for (int RC = 32; RC >= 8; RC >>= 1) {
+        if (RC > 8 && ((size_t)RC * row > 32768 || RC / 2 >= L.CW)) continue;    // chunks of <= 32 KB, not wider than the part
+        size_t w_st = al128((size_t)RC * row);
+        int S = (int)std::min<size_t>(8, avail / w_st);
+        if (S < 2) continue;
+        pl.RC = RC; pl.NCH = (L.CW + RC - 1) / RC; pl.S = S; pl.w_st = w_st;
+        pl.total = (size_t)S * w_st + fixed;
+        return 0;
+    }
+    return 1;
+}
+
+template <int MODE, bool DBG>
+static const void* hp4_fn() { return (const void*)hp_sweep4_kernel<MODE, DBG>; }
+
+static const void* hp4_select(int mode, bool dbg) {
+    const void* fns[2][4] = {{hp4_fn<0, false>(), hp4_fn<1, false>(), hp4_fn<2, false>(), hp4_fn<3, false>()},
+                             {hp4_fn<0, true>(), hp4_fn<1, true>(), hp4_fn<2, true>(), hp4_fn<3, true>()}};
+    return fns[dbg ? 1 : 0][mode];
+}
+
+// how many clusters of K CTAs of this kernel the device can hold at the same time (0 on error)
+int hp_sweep4_max_clusters(const HpLayout& L, int b) {
+    int dev = 0, max_smem = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+    Hp4Plan pl;
+    if (hp_sweep4_plan(L, b, (size_t)max_smem, pl)) return 0;
+    const void* fn = hp4_select(0, false);
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L.K * 64); cfg.blockDim = dim3(HP4_THREADS); cfg.dynamicSmemBytes = pl.total;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = L.K; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ncl;
+}
+
+int hp_sweep4_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st) {
+    const HpLayout& L = s->lay;
+    int dev = 0, max_smem = 0;
+    HP_CUDA(cudaGetDevice(&dev));
+    HP_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    Hp4Plan pl;
+    if (hp_sweep4_plan(L, s->b, (size_t)max_smem, pl)) { hp_set_error("sweep: the cluster kernel does not fit this partition"); return 1; }
+    const int mode = a.mode == 0 ? 0 : (a.mode == 2 ? 3 : (a.diag_mode == 0 ? 1 : 2));
+    const void* fn = hp4_select(mode, a.dbg != nullptr);
+    HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L.G); cfg.blockDim = dim3(HP4_THREADS); cfg.dynamicSmemBytes = pl.total; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = L.K; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    void* args[] = {&a, &pl};
+    // cooperative = the driver checks that all clusters are co-resident; profilers that replay the kernel refuse that
+    // combination, so a refused launch is repeated as a plain cluster launch (co-residency was checked at setup)
+    cudaError_t e = getenv("HP_NO_COOP") ? cudaErrorNotSupported : cudaLaunchKernelExC(&cfg, fn, args);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cfg.numAttrs = 1;
+        HP_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    }
+    return 0;
+}

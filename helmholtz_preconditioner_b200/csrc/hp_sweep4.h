@@ -1,0 +1,17 @@
+// Cluster sweep kernel (csrc/hp_sweep4.cu): shared-memory plan and host entry points.
+#pragma once
+#include "hp_internal.cuh"
+
+#define HP4_PL 3          // separators per lane in the gather of x: P-1 <= 32*HP4_PL
+#define HP4_EW 3          // gathered entries per warp and batch (one batch when ceil(3b/K) <= 4*HP4_EW)
+
+struct Hp4Plan {
+    int RC, NCH, S;                 // rows per W chunk (power of two), chunks per strip, slots of the W ring
+    size_t w_st, g_st, n_st, r_st;  // stage strides in bytes (multiples of 128)
+    size_t total;                   // dynamic shared memory per CTA
+};
+
+struct HpSweepArgs;
+int hp_sweep4_plan(const HpLayout& L, int b, size_t max_smem, Hp4Plan& pl);
+int hp_sweep4_max_clusters(const HpLayout& L, int b);
+int hp_sweep4_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st);

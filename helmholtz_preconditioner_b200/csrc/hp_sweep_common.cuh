@@ -11,14 +11,14 @@ struct HpSweepArgs {
     const int *leaf_start, *leaf_q, *sep;
     const cplx* packets;
     const cplx* mleaf;        // transfer matrices [strip][dir][leaf][2b][2b] (pipelined kernel)
-    const cplx* qmat;         // one-hop recurrence matrices [strip][dir][G][NR][NSP]
+    const cplx* rsep;         // separator recurrence rows [strip][dir][P-1][b][3b] (cluster kernel)
     int m_lo;
     int mode, m_from, m_to, diag_mode;
     cplx* u;
     const cplx* vin;
     cplx* yout;
     cplx* xch;                // exchange ring: HP_RING slots of slot_stride complex numbers
-    size_t oGP, oGR, oXS, oVS, slot_stride;
+    size_t oGP, oGR, oXS, oVS, slot_stride;      // (cluster kernel: oXS = partial x [P-1][K*NRQ], oGP = gf partials [P][K][b])
     unsigned int* bar;        // [1] abort flag (a spin ran into HP_SPIN_LIMIT)
     const cplx *s2t, *is1t;
     double ih2;
@@ -45,6 +45,11 @@ __device__ __forceinline__ bool xtry(const cplx* p, cplx& v) {
     v.y = __longlong_as_double((long long)hi);
     return lo != HP_SENTINEL && hi != HP_SENTINEL;
 }
+// the load alone (issue several back to back, then test with xvalid)
+__device__ __forceinline__ void xload(const cplx* p, unsigned long long& lo, unsigned long long& hi) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+}
+__device__ __forceinline__ bool xvalid(unsigned long long lo, unsigned long long hi) { return lo != HP_SENTINEL && hi != HP_SENTINEL; }
 // spin until the word is valid; on a runaway spin raise the abort flag (the kernel then terminates)
 __device__ __forceinline__ cplx xget(const cplx* p, unsigned int* abort_flag) {
     cplx v;

@@ -21,6 +21,7 @@ from . import _lib, fields
 from .gmres import DeviceVectors, gmres
 
 DIAG_MODES = {"reference": 0, "paper": 1}
+LAYOUT_MODES = {"auto": 0, "classic": 1, "cluster": 2}
 
 
 def _ptr(t):
@@ -104,8 +105,10 @@ class HelmholtzSolver:
         return out
 
     # ---- preconditioner -------------------------------------------------------------------------------
-    def setup_preconditioner(self, P=0, K=0, m_lo=0, m_hi=0):
-        """algo2_3.  (m_lo, m_hi) = (0, 0): all strips b+1..n; otherwise the strips of this rank's slab."""
+    def setup_preconditioner(self, P=0, K=0, m_lo=0, m_hi=0, layout="auto"):
+        """algo2_3.  (m_lo, m_hi) = (0, 0): all strips b+1..n; otherwise the strips of this rank's slab.
+        layout: "auto" (cluster when a partition exists), "classic", "cluster" (include/helmholtz_b200.h)."""
+        _lib.check(self.lib.hp_set_layout_mode(self.handle, LAYOUT_MODES[layout]), "hp_set_layout_mode")
         _lib.check(self.lib.hp_precond_setup(self.handle, P, K, m_lo, m_hi, _stream()), "hp_precond_setup")
         if m_lo == 0 and m_hi == 0:
             m_lo, m_hi = self.b + 1, self.n
@@ -113,7 +116,7 @@ class HelmholtzSolver:
         return self
 
     def set_sweep_variant(self, variant):
-        """0 = automatic (TMA-staged packets when they fit), 1 = direct global loads."""
+        """0 = automatic; classic layout: 1 direct, 2 TMA staged, 3 pipelined; cluster layout: 4."""
         _lib.check(self.lib.hp_set_sweep_variant(self.handle, int(variant)), "hp_set_sweep_variant")
         return self
 
@@ -139,8 +142,12 @@ class HelmholtzSolver:
         sp = (C.c_int * max(P.value - 1, 1))()
         _lib.check(self.lib.hp_strip_layout(self.handle, None, None, None, None, None, None, None, ls, lq, sp),
                    "hp_strip_layout")
+        colN, NCB, NRQ, NXG = (C.c_int() for _ in range(4))
+        _lib.check(self.lib.hp_strip_layout_ex(self.handle, C.byref(colN), C.byref(NCB), C.byref(NRQ), C.byref(NXG)),
+                   "hp_strip_layout_ex")
         return dict(P=P.value, K=K.value, G=P.value * K.value, QP=QP.value, CW=CW.value, NS=NS.value, NR=NR.value,
-                    PK=PK.value, leaf_start=np.array(ls[:]), q=np.array(lq[:]), sep=np.array(sp[:P.value - 1]))
+                    PK=PK.value, leaf_start=np.array(ls[:]), q=np.array(lq[:]), sep=np.array(sp[:P.value - 1]),
+                    colN=colN.value, NCB=NCB.value, NRQ=NRQ.value, NXG=NXG.value)
 
     def strip_packets(self, m):
         L = self.layout()
@@ -232,9 +239,9 @@ def build_A_matrix(b, const, eta, omega, h, n, c_mat, device=None):
     return _solver_for(b, const, eta, omega, h, n, c_mat, device).assemble_csr()
 
 
-def algo2_3(b, const, eta, omega, h, n, c_mat, device=None, P=0, K=0):
+def algo2_3(b, const, eta, omega, h, n, c_mat, device=None, P=0, K=0, layout="auto"):
     """code.py:345-353.  Returns (lu_HF, lu_Hm_ra): both are the same factorisation handle here."""
-    s = _solver_for(b, const, eta, omega, h, n, c_mat, device).setup_preconditioner(P, K)
+    s = _solver_for(b, const, eta, omega, h, n, c_mat, device).setup_preconditioner(P, K, layout=layout)
     return s, s
 
 

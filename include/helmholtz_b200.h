@@ -68,8 +68,13 @@ int hp_precond_setup(hp_solver* s, int P, int K, int m_lo, int m_hi, void* strea
 /* bytes of device memory held by the strip factorisation, and the device time the last setup took */
 int64_t hp_precond_bytes(hp_solver* s);
 double hp_precond_setup_ms(hp_solver* s);
-/* sweep kernel variant: 0 = automatic, 1 = direct loads, 2 = TMA-staged block-synchronous, 3 = pipelined with two
- * hand-overs per strip, 4 = pipelined with one hand-over per strip (default when its rings and matrices fit) */
+/* generator layout used by the next hp_precond_setup: 0 = automatic (cluster when a partition exists), 1 = classic
+ * (one CTA per leaf part, N distributed by rows), 2 = cluster (a leaf is a thread-block cluster of K <= 8 CTAs, N
+ * distributed by separator columns; fails when no such partition fits) */
+int hp_set_layout_mode(hp_solver* s, int mode);
+/* sweep kernel variant: 0 = automatic; classic layout: 1 = direct loads, 2 = TMA-staged block-synchronous,
+ * 3 = pipelined with two hand-overs through L2 per strip; cluster layout: 4 = one hand-over through L2 per strip, the
+ * exchanges inside a leaf through distributed shared memory */
 int hp_set_sweep_variant(hp_solver* s, int variant);
 /* 0 = fine; 1 = a sweep kernel gave up waiting for data from another CTA (a bug, never expected); synchronises */
 int hp_sweep_status(hp_solver* s);
@@ -95,6 +100,9 @@ int hp_strip_apply(hp_solver* s, int m, const double* v_dev, double* y_dev, void
 int hp_strip_layout(hp_solver* s, int* P, int* K, int* QP, int* CW, int* NS, int* NR, int64_t* PK,
                     int* leaf_start_host /* P */, int* leaf_q_host /* P */, int* sep_host /* P-1 */);
 int hp_strip_packets(hp_solver* s, int m, double* packets_host);
+/* cluster layout details: colN = 1 when N is stored by separator columns ([b][NRQ] per CTA), NCB/NRQ/NXG = separator
+ * right-hand sides, rows of x and gathered entries per CTA */
+int hp_strip_layout_ex(hp_solver* s, int* colN, int* NCB, int* NRQ, int* NXG);
 
 /* ---- Krylov vector kernels (scipy gmres inner loop, iterative.py; called from code.py:516) -------- */
 

@@ -39,17 +39,35 @@ def test_strips_4096_vs_oracle(hp):
     import scipy.sparse.linalg as spla
     for m_lo in (b + 1, n // 2, n - 1):
         m_hi = min(n, m_lo + 1)
-        s.setup_preconditioner(m_lo=m_lo, m_hi=m_hi)
+        refs = {}
         for m in (m_lo, m_hi):
-            v = rnd(n, m)
             lu = spla.splu(orc.get_Hm(m, b, const, b * h, omega, h, n, c_mat).tocsc())
             t = np.zeros(b * n, complex)
-            t[-n:] = v.cpu().numpy()
-            ref = lu.solve(t)[-n:]
-            for variant in (1, 2, 3, 4):
-                s.set_sweep_variant(variant)
-                assert rel(s.strip_apply(m, v), ref) < 1e-11
+            t[-n:] = rnd(n, m).cpu().numpy()
+            refs[m] = lu.solve(t)[-n:]
+        for layout in ("classic", "auto"):
+            s.setup_preconditioner(m_lo=m_lo, m_hi=m_hi, layout=layout)
+            for m in (m_lo, m_hi):
+                for variant in variants_of(s):
+                    s.set_sweep_variant(variant)
+                    assert rel(s.strip_apply(m, rnd(n, m)), refs[m]) < 1e-11
+            s.set_sweep_variant(0)
     assert s.sweep_status() == 0
+    s.close()
+
+
+def variants_of(s):
+    return (4,) if s.layout()["colN"] else (1, 2, 3)
+
+
+@pytest.fixture(scope="module")
+def solver1024c(hp):
+    """the same problem as solver1024 with the classic generator layout (sweep kernel variants 1-3)"""
+    n, b = 1024, 20
+    omega = 2 * np.pi * n / 10 + 2j
+    c_mat, f_mat = hp.init_const_f1(omega, n)
+    s = hp.HelmholtzSolver(n, b, omega, 100.0, c_mat).setup_preconditioner(layout="classic")
+    yield s, f_mat
     s.close()
 
 
@@ -64,8 +82,9 @@ def solver1024(hp):
     s.close()
 
 
-def test_strip_operator_properties_1024(solver1024):
-    s, _ = solver1024
+def test_strip_operator_properties_1024(solver1024, solver1024c):
+    s, _ = solver1024c
+    s4, _ = solver1024
     n = s.n
     v1, v2 = rnd(n, 1), rnd(n, 2)
     for m in (s.b + 1, 500, n):
@@ -81,15 +100,16 @@ def test_strip_operator_properties_1024(solver1024):
         yd = s.strip_apply(m, v1)
         s.set_sweep_variant(2)
         assert torch.equal(s.strip_apply(m, v1), yd)
-        for variant in (3, 4):
-            s.set_sweep_variant(variant)
-            assert rel(s.strip_apply(m, v1), yd) < 1e-13
+        s.set_sweep_variant(3)
+        assert rel(s.strip_apply(m, v1), yd) < 1e-13
         s.set_sweep_variant(0)
-    assert s.sweep_status() == 0
+        assert rel(s4.strip_apply(m, v1), yd) < 1e-12          # cluster layout: another partition of the strip
+    assert s.sweep_status() == 0 and s4.sweep_status() == 0
 
 
-def test_preconditioner_properties_1024(solver1024):
-    s, f_mat = solver1024
+def test_preconditioner_properties_1024(solver1024, solver1024c):
+    s, f_mat = solver1024c
+    s4, _ = solver1024
     N = s.n ** 2
     x, y = rnd(N, 3), rnd(N, 4)
     Mx, My = s.precond_apply(x), s.precond_apply(y)
@@ -100,14 +120,17 @@ def test_preconditioner_properties_1024(solver1024):
     Md = s.precond_apply(x)
     s.set_sweep_variant(2)
     assert torch.equal(s.precond_apply(x), Md)
-    for variant in (3, 4):
-        s.set_sweep_variant(variant)
-        assert rel(s.precond_apply(x), Md) < 1e-12
+    s.set_sweep_variant(3)
+    assert rel(s.precond_apply(x), Md) < 1e-12
     assert rel(Mx, Md) < 1e-12
     s.set_sweep_variant(0)
+    M4 = s4.precond_apply(x)
+    assert rel(M4, Md) < 1e-11 and torch.equal(s4.precond_apply(x), M4)
+    assert rel(s4.precond_apply(x, diag="paper"), s.precond_apply(x, diag="paper")) < 1e-11
+    assert rel(s4.precond_apply((0.5 + 2j) * x - y), (0.5 + 2j) * M4 - s4.precond_apply(y)) < 1e-11
     for d in ("reference", "paper"):
         assert torch.isfinite(torch.view_as_real(s.precond_apply(x, diag=d))).all()
-    assert s.sweep_status() == 0
+    assert s.sweep_status() == 0 and s4.sweep_status() == 0
 
 
 def test_matvec_matches_assembled_csr_1024(solver1024):

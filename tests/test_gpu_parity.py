@@ -56,13 +56,14 @@ def test_assembly_golden(hp, path):
     assert relerr(y2, g["A_x_rand"]) < 1e-13
 
 
+@pytest.mark.parametrize("layout", ["classic", "cluster"])
 @pytest.mark.parametrize("n,b,P,K", [(45, 12, 4, 2), (63, 12, 5, 3), (40, 5, 1, 3), (40, 5, 7, 1), (50, 20, 3, 4)])
-def test_strip_generators_vs_model(hp, n, b, P, K):
+def test_strip_generators_vs_model(hp, n, b, P, K, layout):
     """The packets written by the setup kernels against the numpy model of the same layout."""
     omega = 2 * np.pi * 5 + 2j
     c_mat = orc.init_c1_f1(omega, n)[0]
     s = hp.HelmholtzSolver(n, b, omega, 60.0, c_mat)
-    s.setup_preconditioner(P=P, K=K)
+    s.setup_preconditioner(P=P, K=K, layout=layout)
     h = 1 / (n + 1)
     for m in (b + 1, (n + b) // 2, n):
         L, pk = s.strip_packets(m)
@@ -81,25 +82,42 @@ def test_strip_generators_vs_model(hp, n, b, P, K):
                 assert np.allclose(Wp[:lc1 - lc0, :q], mod.W[l, lc0:lc1, :q], rtol=0, atol=1e-11 * np.abs(mod.W).max())
                 Gm = mod.G[l].reshape(2 * b, -1)[:, lc0:lc1]
                 assert np.allclose(Gp[:, :lc1 - lc0], Gm, rtol=0, atol=1e-11 * max(np.abs(mod.G).max(), 1e-300))
+        assert L["colN"] == (layout == "cluster")
         if NS:
             offN = CW * QP + 2 * b * CW
             N = np.zeros((NS, NS), complex)
-            for row in range(NS):
-                N[row] = pk[row // NR, offN + (row % NR) * NS: offN + (row % NR + 1) * NS]
+            if L["colN"]:
+                NRQ = L["NRQ"]      # CTA (j, k) holds N[NRQ*k : NRQ*(k+1), columns of separator j], column major
+                for j in range(P - 1):
+                    for k in range(K):
+                        blk = pk[j * K + k, offN:offN + b * NRQ].reshape(b, NRQ)
+                        r0, r1 = NRQ * k, min(NS, NRQ * (k + 1))
+                        if r1 > r0:
+                            N[r0:r1, j * b:(j + 1) * b] = blk[:, :r1 - r0].T
+            else:
+                for row in range(NS):
+                    N[row] = pk[row // NR, offN + (row % NR) * NS: offN + (row % NR + 1) * NS]
             assert np.allclose(N, mod.N, rtol=0, atol=1e-11 * np.abs(mod.N).max())
     s.close()
 
 
-@pytest.mark.parametrize("n,b,P,K", [(63, 12, 5, 3), (40, 5, 1, 3), (40, 5, 7, 1), (200, 12, 0, 0), (130, 20, 6, 5)])
-def test_strip_apply_vs_oracle(hp, n, b, P, K):
+def variants_of(s):
+    """sweep kernel variants that can run on the layout the solver was set up with"""
+    return (4,) if s.layout()["colN"] else (1, 2, 3)
+
+
+@pytest.mark.parametrize("layout", ["classic", "auto"])
+@pytest.mark.parametrize("n,b,P,K", [(63, 12, 5, 3), (40, 5, 1, 3), (40, 5, 7, 1), (200, 12, 0, 0), (130, 20, 6, 5), (300, 12, 6, 4),
+                                     (45, 12, 4, 2)])
+def test_strip_apply_vs_oracle(hp, n, b, P, K, layout):
     """y = T_m v against the oracle's splu solve (code.py:368-370)."""
     omega = 2 * np.pi * (n / 10) + 2j
     c_mat = orc.init_c1_f1(omega, n)[0]
     h = 1 / (n + 1)
     Pc = orc.SweepingPreconditioner(b, 60.0, b * h, omega, h, n, c_mat)
-    s = hp.HelmholtzSolver(n, b, omega, 60.0, c_mat).setup_preconditioner(P=P, K=K)
+    s = hp.HelmholtzSolver(n, b, omega, 60.0, c_mat).setup_preconditioner(P=P, K=K, layout=layout)
     rng = np.random.default_rng(3)
-    for variant in (1, 2, 3, 4):
+    for variant in variants_of(s):
         s.set_sweep_variant(variant)
         for m in (b + 1, (n + b) // 2, n - 1, n):
             v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
@@ -171,20 +189,21 @@ def test_krylov_kernels(hp):
     assert relerr(x, w + y @ V) < 1e-13
 
 
-def test_medium_preconditioner_vs_oracle(hp):
+@pytest.mark.parametrize("layout", ["classic", "auto"])
+def test_medium_preconditioner_vs_oracle(hp, layout):
     """n = 255 (the reference's second problem size, code.py:579), automatic partition."""
     n, b, wn, const = 255, 12, 32, 62
     omega = 2 * np.pi * wn + 2j
     h = 1 / (n + 1)
     c_mat, f_mat = orc.init_c1_f1(omega, n)
     Pc = orc.SweepingPreconditioner(b, const, b * h, omega, h, n, c_mat)
-    s, _ = hp.algo2_3(b, const, b * h, omega, h, n, c_mat)
+    s, _ = hp.algo2_3(b, const, b * h, omega, h, n, c_mat, layout=layout)
     f = f_mat.flatten().astype(np.complex128)
     ref = Pc.apply(f)
     Pc.diag = "paper"
     Pc_paper = Pc.apply(f)
     assert relerr(hp.algo2_4(f, b, n, s), ref) < 1e-12
-    for variant in (1, 2, 3, 4):
+    for variant in variants_of(s):
         s.set_sweep_variant(variant)
         assert relerr(hp.algo2_4(f, b, n, s), ref) < 1e-12
         assert relerr(hp.algo2_4(f, b, n, s, diag="paper"), Pc_paper) < 1e-12
