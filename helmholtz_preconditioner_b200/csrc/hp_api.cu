@@ -125,7 +125,7 @@ extern "C" int hp_precond_setup(hp_solver* s, int P, int K, int m_lo, int m_hi, 
 // developer hook: per-phase cycle counters of the sweep kernel.  on=1 allocates/zeroes, read copies [G][8] to host
 extern "C" int hp_debug_phases(hp_solver* s, int on, long long* out_host) {
     if (!s || !s->packets) return 1;
-    size_t sz = sizeof(long long) * ((16 + 64 * 16) * s->lay.G + 2 * 64 * 32);
+    size_t sz = sizeof(long long) * (16 + 64 * 16) * s->lay.G;
     if (on && !s->dbg) { HP_CUDA(cudaMalloc(&s->dbg, sz)); HP_CUDA(cudaMemset(s->dbg, 0, sz)); }
     if (out_host && s->dbg) HP_CUDA(cudaMemcpy(out_host, s->dbg, sz, cudaMemcpyDeviceToHost));
     if (!on && s->dbg) { cudaFree(s->dbg); s->dbg = nullptr; }

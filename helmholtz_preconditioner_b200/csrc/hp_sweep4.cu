@@ -71,7 +71,7 @@ __device__ __forceinline__ void mbar_wait4(unsigned long long* bar, unsigned int
     }
 }
 __device__ __forceinline__ void mbar_arrive_local(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void ring_fill4(unsigned char* dst, const cplx* src, unsigned int bytes, unsigned long long* bar) {
     mbar_expect_tx(bar, bytes);
@@ -80,12 +80,13 @@ __device__ __forceinline__ void ring_fill4(unsigned char* dst, const cplx* src, 
 }
 
 // MODE: 0 forward, 1 backward (reference diagonal), 2 backward (paper diagonal), 3 single strip apply
-template <int MODE, bool DBG>
+// BT, KT: PML width and cluster size as compile-time constants (0 = run-time values)
+template <int MODE, bool DBG, int BT, int KT>
 __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a, Hp4Plan pl) {
     constexpr int a_mode = MODE == 0 ? 0 : (MODE == 3 ? 2 : 1);
     constexpr int a_diag = MODE == 2 ? 1 : 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int b = a.b, b2 = 2 * a.b, b3 = 3 * a.b, n = a.n, K = a.lay.K, P = a.lay.P, QP = a.lay.QP, CW = a.lay.CW;
+    const int b = BT ? BT : a.b, b2 = 2 * b, b3 = 3 * b, n = a.n, K = KT ? KT : a.lay.K, P = a.lay.P, QP = a.lay.QP, CW = a.lay.CW;
     const int NS = a.lay.NS, NRQ = a.lay.NRQ, NXG = a.lay.NXG;
     const int PP = P | 1;                          // partial solutions are stored entry-major [NS][PP]: the lanes of a warp poll
                                                    // the P-1 contributions to one entry with one coalesced load
@@ -213,19 +214,29 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
             for (int ps = 0; ps < NPASS; ++ps) pre[ps] = cmake(0.0, 0.0);
             if (has_sep) {
                 mbar_wait4(&barGL[par], ph, abort_flag, dead);
+                {
+                    unsigned long long glo[NPASS], ghi[NPASS];
+                    unsigned int spins = 0;
+                    for (;;) {                                 // the warp leaves the loop as a whole
+                        bool ok = true;
 #pragma unroll
-                for (int ps = 0; ps < NPASS; ++ps) {
-                    const int e = e_lo + EPP * ps;
-                    if (e < b && part < K) {
-                        cplx gf = cmake(0.0, 0.0);
-                        const cplx* pg = slot + a.oGP + ((size_t)(l + 1) * K + part) * b + e;
-                        unsigned int spins = 0;
-                        while (!xtry(pg, gf)) {
-                            if (*dead) break;
-                            if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; break; }
-                            if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) { *dead = 1u; break; }
+                        for (int ps = 0; ps < NPASS; ++ps) {
+                            const int e = e_lo + EPP * ps;
+                            glo[ps] = ghi[ps] = 0ull;
+                            if (e < b && part < K) xload(slot + a.oGP + ((size_t)(l + 1) * K + part) * b + e, glo[ps], ghi[ps]);
                         }
-                        pre[ps] = cadd(glp[((size_t)par * K + part) * b + e], gf);
+#pragma unroll
+                        for (int ps = 0; ps < NPASS; ++ps) ok = ok && xvalid(glo[ps], ghi[ps]);
+                        if (__all_sync(0xffffffffu, ok || *dead)) break;
+                        if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; }
+                        if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) *dead = 1u;
+                    }
+#pragma unroll
+                    for (int ps = 0; ps < NPASS; ++ps) {
+                        const int e = e_lo + EPP * ps;
+                        if (e < b && part < K)
+                            pre[ps] = cadd(glp[((size_t)par * K + part) * b + e],
+                                           cmake(__longlong_as_double((long long)glo[ps]), __longlong_as_double((long long)ghi[ps])));
                     }
                 }
                 mbar_wait4(&barR[par], ph, abort_flag, dead);
@@ -338,11 +349,6 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                         if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; }
                         if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) *dead = 1u;
                     }
-                    if (DBG && (g == 5 || g == 64) && cw == 0 && it >= 512 && it < 576) {      // per-lane arrival of the gathered words
-                        unsigned long long t_;
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
-                        a.dbg[(size_t)a.lay.G * 16 * 65 + ((size_t)(g == 5 ? 0 : 1) * 64 + (it - 512)) * 32 + lane] = (long long)t_;
-                    }
                     HP_TICK(4);
                     HP_STAMP4(5);
                     cplx sums[HP4_EW];
@@ -412,8 +418,11 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
         // off-path group
         // =====================================================================================================
         const int ot = tid - HP4_CRIT - HP4_PROD, ow = ot >> 5;
-        const bool col = ot < ncols;
-        const int c = c0 + ot;
+        // columns of the part: cpl lanes per column (8 when the part is at most 32 columns wide: the 2b-term correction
+        // is split over the lanes and the K copies of v go out in parallel); every lane of a column keeps the same state
+        const int cpl = CW <= HP4_OFF / 8 ? 8 : 1, cpart = ot & (cpl - 1), oc = cpl == 8 ? ot >> 3 : ot;
+        const bool col = oc < ncols, colw = col && cpart == 0;      // colw: the lane that writes the column's results
+        const int c = c0 + oc;
         const cplx cis1 = col ? a.is1t[2 * (c + 1)] : cmake(0.0, 0.0);
         // per-column state: vbr = vb(t), y0prev = y0(t-1), coefc = multiplier of the correction in v(t),
         // ubase = (backward) original value of the row strip t-1 overwrites
@@ -427,7 +436,7 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                 vbr = ubase;
                 if (m0 < n) vbr = cfma(cscale(sg, cmul(hp_rowfac(a, m0), cis1)), ldcg(a.u + (size_t)m0 * n + c), vbr);
             }
-            vb[ot] = vbr;
+            if (colw) vb[oc] = vbr;
         }
         bar_off4();
         // leaf product: RC/8 rows per warp, LPR lanes per row
@@ -496,26 +505,38 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                     HP_TICK(2);
                     HP_STAMP4(3);
                     const cplx* xa = x3 + (size_t)(par ^ 1) * b3;              // [x_{l-1}; x_l] are its first 2b entries
-                    if (col) {
-                        cplx c1 = cmake(0.0, 0.0), c2 = cmake(0.0, 0.0), c3 = cmake(0.0, 0.0);
-                        int kap = 0;
-#pragma unroll 2
-                        for (; kap + 3 < b2; kap += 4) {
-                            corr = cfma(Gprev[(size_t)kap * CW + ot], xa[kap], corr);
-                            c1 = cfma(Gprev[(size_t)(kap + 1) * CW + ot], xa[kap + 1], c1);
-                            c2 = cfma(Gprev[(size_t)(kap + 2) * CW + ot], xa[kap + 2], c2);
-                            c3 = cfma(Gprev[(size_t)(kap + 3) * CW + ot], xa[kap + 3], c3);
+                    {
+                        cplx c1 = cmake(0.0, 0.0);
+                        if (col) {
+                            int kap = cpart;
+                            for (; kap + cpl < b2; kap += 2 * cpl) {
+                                corr = cfma(Gprev[(size_t)kap * CW + oc], xa[kap], corr);
+                                c1 = cfma(Gprev[(size_t)(kap + cpl) * CW + oc], xa[kap + cpl], c1);
+                            }
+                            if (kap < b2) corr = cfma(Gprev[(size_t)kap * CW + oc], xa[kap], corr);
+                            corr = cadd(corr, c1);
                         }
-                        for (; kap < b2; ++kap) corr = cfma(Gprev[(size_t)kap * CW + ot], xa[kap], corr);
-                        corr = cadd(cadd(corr, c1), cadd(c2, c3));
+                        if (cpl == 8) {
+#pragma unroll
+                            for (int o = 1; o < 8; o <<= 1) {
+                                corr.x += __shfl_xor_sync(0xffffffffu, corr.x, o);
+                                corr.y += __shfl_xor_sync(0xffffffffu, corr.y, o);
+                            }
+                        }
                     }
                 }
                 if (col) v = cfma(coefc, corr, vbr);
                 // ---- c (first half): the leaf's input to every CTA of the cluster, before the field store
-                if (col && live)
-                    for (int j = 0; j < K; ++j)
-                        st_async_cplx(mapa_u32(smem_u32(v_leaf + (size_t)par * QP + lc0 + ot), j), v, mapa_u32(smem_u32(&barV[par]), j));
-                if (col) {
+                if (col && live) {
+                    if (cpl == 8) {
+                        if (cpart < K)
+                            st_async_cplx(mapa_u32(smem_u32(v_leaf + (size_t)par * QP + lc0 + oc), cpart), v, mapa_u32(smem_u32(&barV[par]), cpart));
+                    } else {
+                        for (int j = 0; j < K; ++j)
+                            st_async_cplx(mapa_u32(smem_u32(v_leaf + (size_t)par * QP + lc0 + oc), j), v, mapa_u32(smem_u32(&barV[par]), j));
+                    }
+                }
+                if (colw) {
                     if (a_mode == 2) a.yout[c] = csub(y0prev, corr);
                     else if (a_mode == 0) a.u[(size_t)mp * n + c] = v;                      // row m_{t-1}: final
                     else {
@@ -524,8 +545,13 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                     }
                 }
             } else if (col && live) {
-                for (int j = 0; j < K; ++j)
-                    st_async_cplx(mapa_u32(smem_u32(v_leaf + (size_t)par * QP + lc0 + ot), j), v, mapa_u32(smem_u32(&barV[par]), j));
+                if (cpl == 8) {
+                    if (cpart < K)
+                        st_async_cplx(mapa_u32(smem_u32(v_leaf + (size_t)par * QP + lc0 + oc), cpart), v, mapa_u32(smem_u32(&barV[par]), cpart));
+                } else {
+                    for (int j = 0; j < K; ++j)
+                        st_async_cplx(mapa_u32(smem_u32(v_leaf + (size_t)par * QP + lc0 + oc), j), v, mapa_u32(smem_u32(&barV[par]), j));
+                }
             }
             if (it > 0) {                                    // Gc(it-1) was last read above
                 __syncwarp();
@@ -541,7 +567,10 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
             const cplx* vl = v_leaf + (size_t)par * QP;
             for (int ch = 0; ch < NCH; ++ch) {
                 const int cidx = it * NCH + ch, sl = cidx % S, r0 = ch * RC;
+                long long tw0 = 0;
+                if (DBG && ot == 0) tw0 = clock64();
                 mbar_wait4(&barW[sl], (cidx / S) & 1, abort_flag, dead);
+                if (DBG && ot == 0) tacc[7] += clock64() - tw0;
                 const cplx* Wc = reinterpret_cast<const cplx*>(ringW + (size_t)sl * pl.w_st);
                 cplx acc = cmake(0.0, 0.0), a1 = cmake(0.0, 0.0), a2 = cmake(0.0, 0.0), a3 = cmake(0.0, 0.0);
                 if (r0 + wr_r < ncols) {
@@ -569,7 +598,7 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
             HP_STAMP4(6);
             if (ot == 0 && it + 2 < nsteps) mbar_expect_tx(&barV[par], v_bytes);
             if (col) {
-                cplx y0 = y0s[ot];
+                cplx y0 = y0s[oc];
                 y0prev = y0;
                 if (a_mode == 0) {
                     coefc = cmul(rf_it, cis1);                                 // A_{m+1,m}
@@ -580,7 +609,7 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                     ubase_prev = ubase;
                     ubase = unx;
                 }
-                vb[ot] = vbr;
+                if (colw) vb[oc] = vbr;
             }
             bar_off4();                                      // vb ready, y0s free for the next strip
             HP_TICK(6);
@@ -611,8 +640,8 @@ int hp_sweep4_plan(const HpLayout& L, int b, size_t max_smem, Hp4Plan& pl) {
     if (fixed + 1024 >= max_smem) return 1;
     size_t avail = max_smem - 1024 - fixed;
     size_t row = (size_t)L.QP * sizeof(cplx);
-    for (int RC = 32; RC >= 8; RC >>= 1) {
-        if (RC > 8 && ((size_t)RC * row > 32768 || RC / 2 >= L.CW)) continue;    // chunks of <= 32 KB, not wider than the part
+    for (int RC = 32; RC >= 8; RC >>= 1) {               // few large chunks: every chunk costs a wait and a reduction
+        if (RC > 8 && RC / 2 >= L.CW) continue;                // not wider than the part
         size_t w_st = al128((size_t)RC * row);
         int S = (int)std::min<size_t>(8, avail / w_st);
         if (S < 2) continue;
@@ -623,13 +652,16 @@ int hp_sweep4_plan(const HpLayout& L, int b, size_t max_smem, Hp4Plan& pl) {
     return 1;
 }
 
-template <int MODE, bool DBG>
-static const void* hp4_fn() { return (const void*)hp_sweep4_kernel<MODE, DBG>; }
+template <int MODE, bool DBG, int BT, int KT>
+static const void* hp4_fn() { return (const void*)hp_sweep4_kernel<MODE, DBG, BT, KT>; }
 
-static const void* hp4_select(int mode, bool dbg) {
-    const void* fns[2][4] = {{hp4_fn<0, false>(), hp4_fn<1, false>(), hp4_fn<2, false>(), hp4_fn<3, false>()},
-                             {hp4_fn<0, true>(), hp4_fn<1, true>(), hp4_fn<2, true>(), hp4_fn<3, true>()}};
-    return fns[dbg ? 1 : 0][mode];
+// the reference's PML width (12 in every call of code.py:574-592) with clusters of 4 gets fully unrolled loops
+static const void* hp4_select(int mode, bool dbg, int b, int K) {
+    const void* gen[2][4] = {{hp4_fn<0, false, 0, 0>(), hp4_fn<1, false, 0, 0>(), hp4_fn<2, false, 0, 0>(), hp4_fn<3, false, 0, 0>()},
+                             {hp4_fn<0, true, 0, 0>(), hp4_fn<1, true, 0, 0>(), hp4_fn<2, true, 0, 0>(), hp4_fn<3, true, 0, 0>()}};
+    const void* s12[2][4] = {{hp4_fn<0, false, 12, 4>(), hp4_fn<1, false, 12, 4>(), hp4_fn<2, false, 12, 4>(), hp4_fn<3, false, 12, 4>()},
+                             {hp4_fn<0, true, 12, 4>(), hp4_fn<1, true, 12, 4>(), hp4_fn<2, true, 12, 4>(), hp4_fn<3, true, 12, 4>()}};
+    return (b == 12 && K == 4) ? s12[dbg ? 1 : 0][mode] : gen[dbg ? 1 : 0][mode];
 }
 
 // how many clusters of K CTAs of this kernel the device can hold at the same time (0 on error)
@@ -639,7 +671,7 @@ int hp_sweep4_max_clusters(const HpLayout& L, int b) {
     if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
     Hp4Plan pl;
     if (hp_sweep4_plan(L, b, (size_t)max_smem, pl)) return 0;
-    const void* fn = hp4_select(0, false);
+    const void* fn = hp4_select(0, false, b, L.K);
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total) != cudaSuccess) { cudaGetLastError(); return 0; }
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
     cudaLaunchConfig_t cfg = {};
@@ -661,7 +693,7 @@ int hp_sweep4_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st) {
     Hp4Plan pl;
     if (hp_sweep4_plan(L, s->b, (size_t)max_smem, pl)) { hp_set_error("sweep: the cluster kernel does not fit this partition"); return 1; }
     const int mode = a.mode == 0 ? 0 : (a.mode == 2 ? 3 : (a.diag_mode == 0 ? 1 : 2));
-    const void* fn = hp4_select(mode, a.dbg != nullptr);
+    const void* fn = hp4_select(mode, a.dbg != nullptr, s->b, L.K);
     HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(L.G); cfg.blockDim = dim3(HP4_THREADS); cfg.dynamicSmemBytes = pl.total; cfg.stream = st;

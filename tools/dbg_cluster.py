@@ -58,15 +58,14 @@ else:
             s.lib.hp_debug_phases(s.handle, 1, None)
             u = x.clone()
             s.sweep_forward(u, b + 1, n - 1); torch.cuda.synchronize()
-            raw = np.zeros(L["G"] * (16 + 1024) + 2 * 64 * 32, dtype=np.int64)
+            raw = np.zeros(L["G"] * (16 + 1024), dtype=np.int64)
             s.lib.hp_debug_phases(s.handle, 0, raw.ctypes.data)
             out = raw[:L["G"] * 16].reshape(L["G"], 16)
             os.makedirs("gpurun_out", exist_ok=True)
             np.save("gpurun_out/timeline4.npy", raw[L["G"] * 16:L["G"] * (16 + 1024)].reshape(L["G"], 64, 16))
-            np.save("gpurun_out/lanes4.npy", raw[L["G"] * (16 + 1024):].reshape(2, 64, 32))
             nst = n - 1 - b
             names = ["pre (GL,GF,R)", "A wait x3", "B rho+bar", "C rows", "D poll", "D sum+send", "-", "-",
-                     "a G wait", "a gb", "b wait x3", "b corr+send", "c wait V", "c W", "c tail", "-"]
+                     "a G wait", "a gb", "b wait x3", "b corr+send", "c wait V", "c W", "c tail", "(W chunk waits)"]
             for i, nm in enumerate(names):
                 print(f"   {nm:14s} {out[:, i].mean() / nst:9.0f} {out[:, i].min() / nst:9.0f} {out[:, i].max() / nst:9.0f}")
         s.close()

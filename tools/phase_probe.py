@@ -23,7 +23,7 @@ for variant in (tuple(int(v) for v in sys.argv[5].split(",")) if len(sys.argv) >
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); s.sweep_forward(u, b + 1, n - 1); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    raw = np.zeros(L["G"] * (16 + 1024 + 32), dtype=np.int64)
+    raw = np.zeros(L["G"] * (16 + 1024), dtype=np.int64)
     s.lib.hp_debug_phases(s.handle, 0, raw.ctypes.data)
     out = raw[:L["G"] * 16].reshape(L["G"], 16) if variant >= 3 else np.pad(raw[:L["G"] * 8].reshape(L["G"], 8), ((0, 0), (0, 8)))
     nst = n - 1 - b

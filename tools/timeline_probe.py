@@ -13,7 +13,7 @@ u = torch.from_numpy(f_mat.ravel().astype(np.complex128)).cuda()
 s.sweep_forward(u, b + 1, b + 799); torch.cuda.synchronize()
 s.lib.hp_debug_phases(s.handle, 1, None)
 s.sweep_forward(u, b + 1, b + 799); torch.cuda.synchronize()
-out = np.zeros(G * (16 + 1024 + 32), dtype=np.int64)
+out = np.zeros(G * (16 + 1024), dtype=np.int64)
 s.lib.hp_debug_phases(s.handle, 0, out.ctypes.data)
 st = out[G * 16:].reshape(G, 64, 4).astype(np.float64)
 red = np.arange(G) % K == 0
