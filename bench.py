@@ -295,7 +295,7 @@ def run_b200(args):
                    "d2h_bytes_per_step": u_host.numel() * 16 / args.steps + 16 * 22,
                    "note": "host f -> device, K GMRES iterations, u -> host; per-iteration Hessenberg columns come back every step"},
            "gpu_launches": int(launches),
-           "roofline": {"bound": "hbm", "kernel": "hp_sweep_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+           "roofline": {"bound": "hbm", "kernel": "hp_sweep4_kernel" if L.get("colN") else "hp_sweep2_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "launches_timed": sw_n.value, "avg_launch_ms": sw_ms.value / max(sw_n.value, 1),
                         "algorithmic_bytes_per_launch": sw_b.value / max(sw_n.value, 1),
@@ -306,7 +306,7 @@ def run_b200(args):
                         "frac_of_hbm_peak": asm_bytes / t_asm / 1e9 / peak, "nnz": nnz},
            "clocks": clk,
            "setup": {"seconds_wall": t_setup, "strip_factor_ms_device": s.setup_ms, "factor_bytes": s.precond_bytes,
-                     "partition": {k: int(L[k]) for k in ("P", "K", "G", "QP", "CW", "NS", "NR", "PK")}},
+                     "partition": {k: int(L[k]) for k in ("P", "K", "G", "QP", "CW", "NS", "NR", "PK", "colN", "NRQ", "NXG")}},
            "residual_last": hist[-1] if hist else None}
     if not args.no_tts:
         # time to solution of the reference's literal call (code.py:510-516: M ignores its argument)

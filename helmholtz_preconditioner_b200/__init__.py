@@ -11,7 +11,7 @@ def __getattr__(name):
     if name in ("HelmholtzSolver", "DeviceCSR", "SolveResult", "run_solver", "build_A_matrix", "algo2_3", "algo2_4"):
         from . import solver
         return getattr(solver, name)
-    if name in ("gmres", "DeviceVectors", "lartg"):
-        from . import gmres as g
-        return getattr(g, name)
+    if name in ("gmres", "gmres_batch", "DeviceVectors", "lartg"):
+        import importlib
+        return getattr(importlib.import_module(__name__ + ".gmres"), name)
     raise AttributeError(name)

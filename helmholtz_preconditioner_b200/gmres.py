@@ -99,6 +99,44 @@ def gmres(matvec, psolve, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=No
     matvec(x, out), psolve(x, out): device operators writing into `out`.  b: device vector (local slab).
     Returns (x, info, hist): hist holds what scipy hands to the legacy callback, one entry per inner iteration.
     """
+    gen = gmres_steps(matvec, b, vec=vec, rtol=rtol, atol=atol, restart=restart, maxiter=maxiter, callback=callback,
+                      nglobal=nglobal)
+    try:
+        req = next(gen)
+        while True:
+            psolve(*req)
+            req = gen.send(None)
+    except StopIteration as done:
+        return done.value
+
+
+def gmres_batch(matvec, psolve_batch, bs, *, vec, **kw):
+    """The same iteration for several right-hand sides advanced in lock step: every round collects one preconditioner
+    request (x, out) per unfinished system and hands the list to psolve_batch, which may pipeline them (slab.py sends
+    them through the slabs one behind the other).  Returns [(x, info, hist), ...] in the order of `bs`."""
+    gens = [gmres_steps(matvec, b, vec=vec, **kw) for b in bs]
+    results = [None] * len(bs)
+    reqs = {}
+    for i, g in enumerate(gens):
+        try:
+            reqs[i] = next(g)
+        except StopIteration as done:
+            results[i] = done.value
+    while reqs:
+        order = sorted(reqs)
+        psolve_batch([reqs[i] for i in order])
+        for i in order:
+            try:
+                reqs[i] = gens[i].send(None)
+            except StopIteration as done:
+                results[i] = done.value
+                del reqs[i]
+    return results
+
+
+def gmres_steps(matvec, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None, callback=None, nglobal=None):
+    """Generator form of gmres(): yields (x, out) whenever the preconditioner has to be applied (out = M x) and
+    returns (x, info, hist) through StopIteration."""
     nloc = b.numel()
     n = nglobal if nglobal is not None else nloc
     dev = b.device
@@ -116,7 +154,7 @@ def gmres(matvec, psolve, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=No
     r = torch.empty_like(b)
     av = torch.empty_like(b)
     w = torch.empty_like(b)
-    psolve(b, w)
+    yield (b, w)
     Mb_nrm2 = vec.norm(w)
     ptol_max_factor = 1.0
     ptol = Mb_nrm2 * min(ptol_max_factor, atol / bnrm2)
@@ -130,7 +168,7 @@ def gmres(matvec, psolve, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=No
             vec.scale_copy(1.0, b, r)
             if bnrm2 < atol:
                 return x, 0, hist
-        psolve(r, V[0])
+        yield (r, V[0])
         tmp = vec.norm(V[0])
         vec.scale_copy(1.0 / tmp, V[0], V[0])
         S = np.zeros(restart + 1, dtype=np.complex128)
@@ -139,7 +177,7 @@ def gmres(matvec, psolve, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=No
         col = 0
         for col in range(restart):
             matvec(V[col], av)
-            psolve(av, w)
+            yield (av, w)
             hcol, h1, h0 = vec.mgs(V, col + 1, w)
             hh[col, :col + 1] = hcol
             hh[col, col + 1] = h1
