@@ -42,13 +42,17 @@ def parse():
     ap.add_argument("--cpu-strips", type=int, default=6, help="strips timed for the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tts", action="store_true")
+    ap.add_argument("--mp-mode", default="pipelined", choices=["pipelined", "weak"],
+                    help="N > 1: 'pipelined' = the 4096^2 problem slab-decomposed, 4N right-hand sides sent through the slabs one "
+                         "behind the other; 'weak' = one problem of 4096^2 points per GPU (n = 4096 sqrt(N)), one right-hand side")
+    ap.add_argument("--rhs", type=int, default=0, help="right-hand sides in flight in the pipelined mode (default 4N)")
     return ap.parse_args()
 
 
 def workload(args, world):
     """BASELINE.json configs: N=1 -> 'heterogeneous synthetic layered velocity model 4096^2, preconditioned
     solve, 1 B200' (the configuration the metric is quoted on); N>1 -> weak scaling, 4096^2 points per GPU."""
-    n = args.n if args.n else int(round(4096 * np.sqrt(world)))
+    n = args.n if args.n else (int(round(4096 * np.sqrt(world))) if args.mp_mode == "weak" else 4096)
     wave_num = n / args.ppw
     return dict(n=n, b=args.b, wave_num=wave_num, const=args.const, alpha=2.0, model=args.model)
 

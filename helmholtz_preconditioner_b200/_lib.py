@@ -36,6 +36,7 @@ SIGNATURES = {
     "hp_precond_bytes": (_i64, [_vp]),
     "hp_precond_setup_ms": (_d, [_vp]),
     "hp_front_begin": (_i, [_vp, _vp, _vp]),
+    "hp_front_tf_copy": (_i, [_vp, _vp, _i, _vp]),
     "hp_sweep_forward": (_i, [_vp, _vp, _i, _i, _vp]),
     "hp_sweep_backward": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "hp_front_end": (_i, [_vp, _vp, _vp]),

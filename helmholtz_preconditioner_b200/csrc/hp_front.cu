@@ -169,3 +169,14 @@ extern "C" int hp_front_end(hp_solver* s, double* u_dev, void* stream) {
     HP_CUDA(cudaGetLastError());
     return 0;
 }
+
+// T_F u_F lives in the solver between hp_front_begin and hp_front_end; with several right-hand sides in flight
+// (slab.py pipelines them through the slabs) the caller parks it in its own buffer of b*n complex numbers.
+// dir 0: solver -> buf_dev, dir 1: buf_dev -> solver.
+extern "C" int hp_front_tf_copy(hp_solver* s, double* buf_dev, int dir, void* stream) {
+    if (!s || !s->TF) { hp_set_error("hp_front_tf_copy: preconditioner not set up"); return 1; }
+    size_t sz = sizeof(cplx) * (size_t)s->b * s->n;
+    HP_CUDA(cudaMemcpyAsync(dir == 0 ? (void*)buf_dev : (void*)s->TF, dir == 0 ? (const void*)s->TF : (const void*)buf_dev, sz,
+                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}

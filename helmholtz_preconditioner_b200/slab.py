@@ -43,6 +43,7 @@ class SlabSolver:
         self.m_lo, self.m_hi = max(b + 1, self.j0 + 1), min(n, self.j1)
         # local work buffer with one ghost row below (row j0-1) and above (row j1)
         self.buf = torch.zeros((self.rows + 2) * n, dtype=torch.complex128, device=device)
+        self.bufs, self.tfs = [self.buf], []                 # work buffers / parked T_F u_F of a batch of right-hand sides
         self.south = torch.zeros(n, dtype=torch.complex128, device=device)
         self.north = torch.zeros(n, dtype=torch.complex128, device=device)
 
@@ -53,10 +54,10 @@ class SlabSolver:
     def _recv(self, t, src):
         dist.recv(t, src, group=self.group)
 
-    def _row(self, j):
+    def _row(self, j, buf=None):
         """view of global row j inside the ghosted buffer (j0-1 <= j <= j1)."""
         o = (j - (self.j0 - 1)) * self.n
-        return self.buf[o:o + self.n]
+        return (self.buf if buf is None else buf)[o:o + self.n]
 
     # -- operator -------------------------------------------------------------------------------------
     def matvec(self, x, out):
@@ -111,6 +112,67 @@ class SlabSolver:
         return out
 
 
+    def precond_apply_batch(self, pairs, diag="reference"):
+        """out_i = M x_i for every (x_i, out_i) of `pairs`, the right-hand sides sent through the slabs one behind the
+        other: while rank r sweeps its strips for right-hand side i, rank r+1 sweeps them for i-1.  Per sweep direction
+        a batch of R takes (world - 1 + R) slab sweeps instead of R * world, the rows handed over are posted as
+        non-blocking sends so that a rank goes on with the next right-hand side at once."""
+        n, b, r, w = self.n, self.b, self.rank, self.world
+        R = len(pairs)
+        while len(self.bufs) < R:
+            self.bufs.append(torch.zeros_like(self.buf))
+        if r == 0 and hasattr(self.s, "front_tf_new"):
+            while len(self.tfs) < R:
+                self.tfs.append(self.s.front_tf_new())
+        row0 = self.j0 - 1
+        owns = [self.bufs[i][n:(self.rows + 1) * n] for i in range(R)]
+        for i, (x, _) in enumerate(pairs):
+            owns[i].copy_(x)
+        # ghost rows above (initial values of the first row of the next slab), all right-hand sides in one batch
+        if w > 1:
+            ops = []
+            for i in range(R):
+                if r > 0:
+                    ops.append(dist.P2POp(dist.isend, owns[i][:n], r - 1, self.group))
+                if r < w - 1:
+                    ops.append(dist.P2POp(dist.irecv, self._row(self.j1, self.bufs[i]), r + 1, self.group))
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
+        sends = []
+        m_to = min(self.m_hi, n - 1)
+        for i in range(R):                                   # forward chain
+            buf = self.bufs[i]
+            if r == 0:
+                self.s.front_begin_buf(buf, row0)
+                if R > 1:
+                    self.s.front_tf_save(self.tfs[i])
+            else:
+                self._recv(self._row(self.j0, buf), r - 1)
+            if self.m_lo <= m_to:
+                self.s.sweep_forward_buf(buf, row0, self.m_lo, m_to)
+            if r < w - 1:
+                sends.append(dist.isend(self._row(self.j1, buf), r + 1, group=self.group))
+        for q in sends:                                      # the rows come back in the backward chain
+            q.wait()
+        sends = []
+        for i in range(R):                                   # backward chain
+            buf = self.bufs[i]
+            if r < w - 1:
+                self._recv(self._row(self.j1, buf), r + 1)
+            if self.m_lo <= self.m_hi:
+                self.s.sweep_backward_buf(buf, row0, self.m_hi, self.m_lo, diag)
+            if r > 0:
+                sends.append(dist.isend(self._row(self.j0, buf), r - 1, group=self.group))
+            else:
+                if R > 1:
+                    self.s.front_tf_load(self.tfs[i])
+                self.s.front_end_buf(buf, row0)
+        for q in sends:
+            q.wait()
+        for i, (_, out) in enumerate(pairs):
+            out.copy_(owns[i])
+
+
 def distributed_gmres_setup(n, b, omega, const, c_mat, rank, world, group, device, P=0, K=0):
     """HelmholtzSolver of this rank with its strips factored, wrapped in a SlabSolver."""
     from .solver import HelmholtzSolver
@@ -122,12 +184,16 @@ def distributed_gmres_setup(n, b, omega, const, c_mat, rank, world, group, devic
 
 
 def bench_distributed(args, w, make_fields, config_dict, ClockSampler):
-    """bench.py for N > 1: weak scaling, one slab per rank, GMRES(20) inner iterations of the global problem."""
+    """bench.py for N > 1.  One slab of the grid per rank; Krylov vectors, SpMV halo rows and dot products distributed.
+    mode 'pipelined' (default): the 4096^2 problem, R = 4N right-hand sides (the reference's source, shifted) advance
+    in lock step, their preconditioner applications pipelined through the slabs (precond_apply_batch); value = all
+    GMRES(20) inner iterations of all right-hand sides per second.  mode 'weak': one right-hand side of a problem
+    with 4096^2 points per GPU (the sweeps then run one slab after the other)."""
     import json
     import os
     import time
     from . import _lib
-    from .gmres import DeviceVectors, gmres
+    from .gmres import DeviceVectors, gmres, gmres_batch
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -135,20 +201,27 @@ def bench_distributed(args, w, make_fields, config_dict, ClockSampler):
     omega, c_mat, f_mat = make_fields(w)
     n, b = w["n"], w["b"]
     dev = torch.device(f"cuda:{local}")
+    pipelined = args.mp_mode == "pipelined"
+    R = (args.rhs if args.rhs > 0 else 4 * world) if pipelined else 1
     t0 = time.time()
     S = distributed_gmres_setup(n, b, omega, w["const"], c_mat, rank, world, None, dev)
     torch.cuda.synchronize()
     t_setup = time.time() - t0
-    f_loc_host = torch.from_numpy(np.ascontiguousarray(f_mat[S.j0:S.j1].ravel())).pin_memory()
-    f = f_loc_host.to(dev)
-    vec = DeviceVectors(f.numel(), dev, group=dist.group.WORLD)
+    # right-hand sides: the source of the reference moved along x1 (one shot position per right-hand side)
+    f_hosts = [torch.from_numpy(np.ascontiguousarray(np.roll(f_mat, (i * n) // (2 * R), axis=1)[S.j0:S.j1].ravel())).pin_memory()
+               for i in range(R)]
+    fs = [fh.to(dev) for fh in f_hosts]
+    vec = DeviceVectors(fs[0].numel(), dev, group=dist.group.WORLD)
     mv = lambda x, out: S.matvec(x, out)                       # noqa: E731
+    psb = lambda reqs: S.precond_apply_batch(reqs)             # noqa: E731
     ps = lambda x, out: S.precond_apply(x, out)                # noqa: E731
 
     def iterations(k, rhs):
-        return gmres(mv, ps, rhs, vec=vec, rtol=0.0, atol=0.0, restart=20, maxiter=k, nglobal=n * n)
+        if pipelined:
+            return gmres_batch(mv, psb, rhs, vec=vec, rtol=0.0, atol=0.0, restart=20, maxiter=k, nglobal=n * n)
+        return [gmres(mv, ps, rhs[0], vec=vec, rtol=0.0, atol=0.0, restart=20, maxiter=k, nglobal=n * n)]
 
-    iterations(args.warmup, f)
+    iterations(args.warmup, fs)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -156,20 +229,21 @@ def bench_distributed(args, w, make_fields, config_dict, ClockSampler):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); dist.barrier()
     e0.record()
-    u, info, hist = iterations(args.steps, f)
+    res = iterations(args.steps, fs)
     e1.record()
     torch.cuda.synchronize(); dist.barrier()
     t_dev = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)
     dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     launches = torch.tensor([lib.hp_launch_count() - l0], device=dev)
     dist.all_reduce(launches)
-    # end to end: host slab of f -> device, K iterations, slab of u -> host
-    u_host = torch.empty(f.numel(), dtype=torch.complex128).pin_memory()
+    # end to end: host slabs of every f -> device, K iterations each, slabs of every u -> host
+    u_hosts = [torch.empty(fs[0].numel(), dtype=torch.complex128).pin_memory() for _ in range(R)]
     torch.cuda.synchronize(); dist.barrier()
     e0.record()
-    f2 = f_loc_host.to(dev, non_blocking=True)
-    u2, _, _ = iterations(args.steps, f2)
-    u_host.copy_(u2, non_blocking=True)
+    fs2 = [fh.to(dev, non_blocking=True) for fh in f_hosts]
+    res2 = iterations(args.steps, fs2)
+    for uh, (u2, _, _) in zip(u_hosts, res2):
+        uh.copy_(u2, non_blocking=True)
     e1.record()
     torch.cuda.synchronize(); dist.barrier()
     t_e2e = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)
@@ -178,16 +252,24 @@ def bench_distributed(args, w, make_fields, config_dict, ClockSampler):
     dist.all_reduce(fb)
     if rank == 0:
         clk = clocks.stop()
-        out = {"metric": "precond. Krylov iters/s at 4096^2 2D", "value": args.steps / t_dev.item(), "unit": "iters/s",
+        total_steps = args.steps * R
+        cfg = config_dict(w, world)
+        cfg["parallelism"] = (f"slab{world}, {R} right-hand sides pipelined through the slabs" if pipelined
+                              else f"slab{world}, one right-hand side, 4096^2 points per GPU")
+        cfg["rhs_in_flight"] = R
+        out = {"metric": "precond. Krylov iters/s at 4096^2 2D", "value": total_steps / t_dev.item(), "unit": "iters/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev.item() / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)",
-               "data": "synthetic", "config": config_dict(w, world),
-               "e2e": {"value": args.steps / t_e2e.item(), "unit": "iters/s",
-                       "h2d_bytes_per_step": n * n * 16 / args.steps, "d2h_bytes_per_step": n * n * 16 / args.steps + 16 * 22},
+               "data": "synthetic", "config": cfg,
+               "e2e": {"value": total_steps / t_e2e.item(), "unit": "iters/s",
+                       "h2d_bytes_per_step": R * n * n * 16 / args.steps, "d2h_bytes_per_step": R * (n * n * 16 / args.steps + 16 * 22)},
                "gpu_launches": int(launches.item()), "clocks": clk,
                "setup": {"seconds_wall": t_setup, "factor_bytes_all_ranks": fb.item()},
-               "note": ("weak scaling: 4096^2 grid points per GPU, one global problem of n^2 points; the sweeps of the "
-                        "preconditioner are a sequential chain over the strips, so the slabs take turns (DESIGN.md, multi-GPU)"),
-               "residual_last": hist[-1] if hist else None}
+               "note": ("a step = one GMRES(20) inner iteration of every right-hand side in flight; value counts all of them.  "
+                        "The sweeps of the preconditioner are a sequential chain over the strips, hence over the slabs: one "
+                        "right-hand side keeps one GPU busy at a time, so the right-hand sides follow each other through "
+                        "the slabs (DESIGN.md, multi-GPU); --mp-mode weak runs the single-right-hand-side weak scaling "
+                        "case of BASELINE.json instead"),
+               "residual_last": res[0][2][-1] if res[0][2] else None}
         print(json.dumps(out))
     dist.destroy_process_group()

@@ -181,6 +181,16 @@ class HelmholtzSolver:
     def front_end_buf(self, buf, row0):
         _lib.check(self.lib.hp_front_end(self.handle, self._base(buf, row0), _stream()), "hp_front_end")
 
+    def front_tf_new(self):
+        """buffer that can park T_F u_F of one right-hand side (front_tf_save / front_tf_load)"""
+        return torch.empty(self.b * self.n, dtype=torch.complex128, device=self.device)
+
+    def front_tf_save(self, t):
+        _lib.check(self.lib.hp_front_tf_copy(self.handle, _ptr(t), 0, _stream()), "hp_front_tf_copy")
+
+    def front_tf_load(self, t):
+        _lib.check(self.lib.hp_front_tf_copy(self.handle, _ptr(t), 1, _stream()), "hp_front_tf_copy")
+
     def sweep_forward_buf(self, buf, row0, m_from, m_to):
         _lib.check(self.lib.hp_sweep_forward(self.handle, self._base(buf, row0), m_from, m_to, _stream()), "hp_sweep_forward")
 

@@ -92,6 +92,9 @@ int hp_front_begin(hp_solver* s, double* u_dev, void* stream);
 int hp_sweep_forward(hp_solver* s, double* u_dev, int m_from, int m_to, void* stream);
 int hp_sweep_backward(hp_solver* s, double* u_dev, int m_from, int m_to, int diag_mode, void* stream);
 int hp_front_end(hp_solver* s, double* u_dev, void* stream);
+/* park / restore T_F u_F (b*n complex numbers) between hp_front_begin and hp_front_end when several right-hand
+ * sides are in flight: dir 0 copies solver -> buf_dev, dir 1 copies buf_dev -> solver */
+int hp_front_tf_copy(hp_solver* s, double* buf_dev, int dir, void* stream);
 int hp_precond_apply(hp_solver* s, const double* f_dev, double* u_dev, int diag_mode, void* stream);
 /* y = T_m v : last n entries of H_m^{-1} [0; v]  (lu_Hm_ra[m-b-1].solve(u_temp)[-n:], code.py:370) */
 int hp_strip_apply(hp_solver* s, int m, const double* v_dev, double* y_dev, void* stream);

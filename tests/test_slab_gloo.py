@@ -39,6 +39,15 @@ class NumpyBackend:
         Au[-n:] = self.P.up[b - 1] * u[b - r0]
         u[0 - r0:b - r0] = (self.TF - self.P.lu_HF.solve(Au)).reshape(b, n)
 
+    def front_tf_new(self):
+        return [None]
+
+    def front_tf_save(self, t):
+        t[0] = self.TF.copy()
+
+    def front_tf_load(self, t):
+        self.TF = t[0]
+
     def sweep_forward_buf(self, buf, row0, m_from, m_to):
         u, r0 = self._rows(buf, row0)
         for m in range(m_from, m_to + 1):
@@ -87,7 +96,15 @@ def _worker(rank, world, port, n, b, ret):
     S.matvec(xl, out)
     ref2 = orc.stencil_matvec(x.ravel(), **be.p).reshape(n, n)[S.j0:S.j1].ravel()
     e2 = np.linalg.norm(out.numpy() - ref2) / np.linalg.norm(ref2)
-    ret[rank] = (e1, e2, S.m_lo, S.m_hi)
+    # a batch of right-hand sides pipelined through the slabs: the same results, one by one
+    xs = [rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)) for _ in range(3)]
+    pairs = [(torch.from_numpy(xx[S.j0:S.j1].ravel().copy()), torch.empty_like(xl)) for xx in xs]
+    S.precond_apply_batch(pairs)
+    e3 = 0.0
+    for xx, (_, o) in zip(xs, pairs):
+        refb = be.P.apply(xx.ravel()).reshape(n, n)[S.j0:S.j1].ravel()
+        e3 = max(e3, np.linalg.norm(o.numpy() - refb) / np.linalg.norm(refb))
+    ret[rank] = (e1, e2, S.m_lo, S.m_hi, e3)
     dist.destroy_process_group()
 
 
@@ -105,8 +122,8 @@ def test_slab_schedule_matches_oracle(world):
     mp.spawn(_worker, args=(world, _free_port(), n, b, ret), nprocs=world, join=True)
     strips = []
     for r in range(world):
-        e1, e2, m_lo, m_hi = ret[r]
-        assert e1 < 1e-12 and e2 < 1e-13, (r, e1, e2)
+        e1, e2, m_lo, m_hi, e3 = ret[r]
+        assert e1 < 1e-12 and e2 < 1e-13 and e3 < 1e-12, (r, e1, e2, e3)
         strips += list(range(m_lo, m_hi + 1))
     assert strips == list(range(b + 1, n + 1))      # every strip has exactly one owner
 

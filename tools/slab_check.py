@@ -23,6 +23,18 @@ out = torch.empty_like(xl)
 res = {}
 S.precond_apply(xl, out); res["M"] = out.clone()
 S.matvec(xl, out); res["A"] = out.clone()
+# batch of right-hand sides pipelined through the slabs == one by one
+xs = [torch.from_numpy((rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))[S.j0:S.j1].ravel().copy()).to(dev) for _ in range(5)]
+singles = []
+for xx in xs:
+    o = torch.empty_like(xx); S.precond_apply(xx, o); singles.append(o)
+pairs = [(xx, torch.empty_like(xx)) for xx in xs]
+S.precond_apply_batch(pairs)
+eb = max((torch.linalg.norm(o - s1_) / torch.linalg.norm(s1_)).item() for (_, o), s1_ in zip(pairs, singles))
+ebt = torch.tensor([eb], device=dev); dist.all_reduce(ebt, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(f"batch of 5 pipelined vs one by one: max rel diff {ebt.item():.2e}")
+assert ebt.item() < 1e-13
 vec = DeviceVectors(xl.numel(), dev, group=dist.group.WORLD)
 fl = torch.from_numpy(f_mat[S.j0:S.j1].ravel().astype(np.complex128)).to(dev)
 u, info, hist = gmres(lambda a, o: S.matvec(a, o), lambda a, o: S.precond_apply(a, o, diag="paper"), fl, vec=vec,
