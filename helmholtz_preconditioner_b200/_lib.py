@@ -47,6 +47,7 @@ SIGNATURES = {
     "hp_dotc": (_i, [_i64, _vp, _vp, _vp, _vp]),
     "hp_nrm2": (_i, [_i64, _vp, _vp, _vp]),
     "hp_axpy": (_i, [_i64, _d, _d, _vp, _vp, _vp]),
+    "hp_axpy_dev": (_i, [_i64, _vp, _d, _vp, _vp, _vp]),
     "hp_scale_copy": (_i, [_i64, _d, _d, _vp, _vp, _vp]),
     "hp_mgs": (_i, [_i64, _i, _vp, _i64, _vp, _vp, _vp]),
     "hp_combine": (_i, [_i64, _i, _vp, _i64, _vp, _vp, _vp]),

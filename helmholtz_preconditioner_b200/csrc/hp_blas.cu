@@ -142,6 +142,13 @@ extern "C" int hp_axpy(int64_t n, double a_re, double a_im, const double* x, dou
     return 0;
 }
 
+// y += sign * (*alpha_dev) x with the scalar read from device memory (distributed Gram-Schmidt: no host round trip)
+extern "C" int hp_axpy_dev(int64_t n, const double* alpha_dev, double sign, const double* x, double* y, void* stream) {
+    hp_count_launch(); hp_axpy_dev_kernel<<<hp_ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, (const cplx*)alpha_dev, sign, (const cplx*)x, (cplx*)y);
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int hp_scale_copy(int64_t n, double a_re, double a_im, const double* x, double* y, void* stream) {
     hp_count_launch(); hp_scale_copy_kernel<<<hp_ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, cmake(a_re, a_im), (const cplx*)x, (cplx*)y);
     HP_CUDA(cudaGetLastError());

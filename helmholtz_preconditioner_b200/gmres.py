@@ -78,13 +78,19 @@ class DeviceVectors:
             _lib.check(self.lib.hp_mgs(self.nloc, k, _ptr(V), V.stride(0), _ptr(w), _ptr(self.scal), _stream()), "hp_mgs")
             h = self.scal[:k + 2].cpu().numpy()
             return h[:k].copy(), float(h[k].real), float(h[k + 1].real)
-        h0 = self.norm(w)
-        h = np.zeros(k, dtype=np.complex128)
+        # distributed: the coefficients stay on the device (dot -> all-reduce -> axpy with a device scalar), one
+        # copy to the host at the end
+        import torch.distributed as dist
+        sc = self.scal
+        _lib.check(self.lib.hp_dotc(self.nloc, _ptr(w), _ptr(w), _ptr(sc[k + 1:]), _stream()), "hp_dotc")
         for j in range(k):
-            _lib.check(self.lib.hp_dotc(self.nloc, _ptr(V[j]), _ptr(w), _ptr(self.scal), _stream()), "hp_dotc")
-            h[j] = complex(self._reduce(self.scal[:1])[0].item())
-            self.axpy(-h[j], V[j], w)
-        return h, self.norm(w), h0
+            _lib.check(self.lib.hp_dotc(self.nloc, _ptr(V[j]), _ptr(w), _ptr(sc[j:]), _stream()), "hp_dotc")
+            dist.all_reduce(torch.view_as_real(sc[j:j + 1]), group=self.group)
+            _lib.check(self.lib.hp_axpy_dev(self.nloc, _ptr(sc[j:]), -1.0, _ptr(V[j]), _ptr(w), _stream()), "hp_axpy_dev")
+        _lib.check(self.lib.hp_dotc(self.nloc, _ptr(w), _ptr(w), _ptr(sc[k:]), _stream()), "hp_dotc")
+        dist.all_reduce(torch.view_as_real(sc[k:k + 2]), group=self.group)
+        h = sc[:k + 2].cpu().numpy()
+        return h[:k].copy(), math.sqrt(float(h[k].real)), math.sqrt(float(h[k + 1].real))
 
     def combine(self, V, y, x):
         """x += sum_j y[j] V[j]."""

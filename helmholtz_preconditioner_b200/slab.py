@@ -22,9 +22,19 @@ import torch.distributed as dist
 os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
 
 
-def slab_bounds(n, b, world):
-    """R[0..world]: rank r owns rows R[r]..R[r+1]-1.  Rank 0 must own rows 0..b (front block + row b)."""
-    R = [(n * r) // world for r in range(world + 1)]
+def slab_bounds(n, b, world, front_equiv=0):
+    """R[0..world]: rank r owns rows R[r]..R[r+1]-1.  Rank 0 must own rows 0..b (front block + row b).
+    front_equiv > 0 balances the pipelined sweeps: the front solves of rank 0 cost as much as that many strips, so
+    rank 0 gets that many strips less than its share (strip m belongs to the owner of row m-1)."""
+    if front_equiv <= 0 or world == 1:
+        R = [(n * r) // world for r in range(world + 1)]
+    else:
+        strips = n - b                                        # m = b+1..n, inputs in rows b..n-1
+        share = (strips + front_equiv) / world
+        first = max(1, min(strips - (world - 1), int(round(share - front_equiv))))   # strips of rank 0
+        rest = strips - first
+        R = [0] + [b + first + (rest * r) // (world - 1) for r in range(world)]
+        R[-1] = n
     if world > 1 and R[1] < b + 1:
         raise ValueError(f"slab of rank 0 ({R[1]} rows) must contain the front block and one more row ({b + 1} rows)")
     return R
@@ -33,9 +43,9 @@ def slab_bounds(n, b, world):
 class SlabSolver:
     """Distributed operator/preconditioner on slab-distributed vectors (local shape (rows, n), flattened)."""
 
-    def __init__(self, backend, n, b, rank, world, group=None, device="cpu"):
+    def __init__(self, backend, n, b, rank, world, group=None, device="cpu", front_equiv=0):
         self.s, self.n, self.b, self.rank, self.world, self.group = backend, n, b, rank, world, group
-        self.R = slab_bounds(n, b, world)
+        self.R = slab_bounds(n, b, world, front_equiv)
         self.j0, self.j1 = self.R[rank], self.R[rank + 1]
         self.rows = self.j1 - self.j0
         self.device = device
@@ -173,14 +183,14 @@ class SlabSolver:
             out.copy_(owns[i])
 
 
-def distributed_gmres_setup(n, b, omega, const, c_mat, rank, world, group, device, P=0, K=0):
+def distributed_gmres_setup(n, b, omega, const, c_mat, rank, world, group, device, P=0, K=0, front_equiv=0):
     """HelmholtzSolver of this rank with its strips factored, wrapped in a SlabSolver."""
     from .solver import HelmholtzSolver
     s = HelmholtzSolver(n, b, omega, const, c_mat, device=device)
-    R = slab_bounds(n, b, world)
+    R = slab_bounds(n, b, world, front_equiv)
     m_lo, m_hi = max(b + 1, R[rank] + 1), min(n, R[rank + 1])
     s.setup_preconditioner(P, K, m_lo, m_hi)
-    return SlabSolver(s, n, b, rank, world, group, device=device)
+    return SlabSolver(s, n, b, rank, world, group, device=device, front_equiv=front_equiv)
 
 
 def bench_distributed(args, w, make_fields, config_dict, ClockSampler):
@@ -204,7 +214,8 @@ def bench_distributed(args, w, make_fields, config_dict, ClockSampler):
     pipelined = args.mp_mode == "pipelined"
     R = (args.rhs if args.rhs > 0 else 4 * world) if pipelined else 1
     t0 = time.time()
-    S = distributed_gmres_setup(n, b, omega, w["const"], c_mat, rank, world, None, dev)
+    # pipelined mode: the two front solves of rank 0 (2 x 1.4 ms) weigh as much as ~330 strips (4.2 us per strip and sweep)
+    S = distributed_gmres_setup(n, b, omega, w["const"], c_mat, rank, world, None, dev, front_equiv=330 if pipelined else 0)
     torch.cuda.synchronize()
     t_setup = time.time() - t0
     # right-hand sides: the source of the reference moved along x1 (one shot position per right-hand side)

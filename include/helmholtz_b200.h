@@ -115,6 +115,8 @@ int hp_dotc(int64_t n, const double* x_dev, const double* y_dev, double* out_dev
 int hp_nrm2(int64_t n, const double* x_dev, double* out_dev, void* stream);
 /* y += alpha x with alpha = (a_re, a_im) on the host */
 int hp_axpy(int64_t n, double a_re, double a_im, const double* x_dev, double* y_dev, void* stream);
+/* y += sign * alpha x, alpha (one complex number) read from device memory */
+int hp_axpy_dev(int64_t n, const double* alpha_dev, double sign, const double* x_dev, double* y_dev, void* stream);
 /* y = alpha x */
 int hp_scale_copy(int64_t n, double a_re, double a_im, const double* x_dev, double* y_dev, void* stream);
 /* Modified Gram-Schmidt of w against the rows V[0..k) (row stride ldv complex entries):
