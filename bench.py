@@ -43,9 +43,9 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tts", action="store_true")
     ap.add_argument("--mp-mode", default="pipelined", choices=["pipelined", "weak"],
-                    help="N > 1: 'pipelined' = the 4096^2 problem slab-decomposed, 4N right-hand sides sent through the slabs one "
+                    help="N > 1: 'pipelined' = the 4096^2 problem slab-decomposed, 8N right-hand sides sent through the slabs one "
                          "behind the other; 'weak' = one problem of 4096^2 points per GPU (n = 4096 sqrt(N)), one right-hand side")
-    ap.add_argument("--rhs", type=int, default=0, help="right-hand sides in flight in the pipelined mode (default 4N)")
+    ap.add_argument("--rhs", type=int, default=0, help="right-hand sides in flight in the pipelined mode (default 8N)")
     return ap.parse_args()
 
 

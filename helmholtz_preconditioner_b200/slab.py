@@ -195,7 +195,7 @@ def distributed_gmres_setup(n, b, omega, const, c_mat, rank, world, group, devic
 
 def bench_distributed(args, w, make_fields, config_dict, ClockSampler):
     """bench.py for N > 1.  One slab of the grid per rank; Krylov vectors, SpMV halo rows and dot products distributed.
-    mode 'pipelined' (default): the 4096^2 problem, R = 4N right-hand sides (the reference's source, shifted) advance
+    mode 'pipelined' (default): the 4096^2 problem, R = 8N right-hand sides (the reference's source, shifted) advance
     in lock step, their preconditioner applications pipelined through the slabs (precond_apply_batch); value = all
     GMRES(20) inner iterations of all right-hand sides per second.  mode 'weak': one right-hand side of a problem
     with 4096^2 points per GPU (the sweeps then run one slab after the other)."""
@@ -212,7 +212,7 @@ def bench_distributed(args, w, make_fields, config_dict, ClockSampler):
     n, b = w["n"], w["b"]
     dev = torch.device(f"cuda:{local}")
     pipelined = args.mp_mode == "pipelined"
-    R = (args.rhs if args.rhs > 0 else 4 * world) if pipelined else 1
+    R = (args.rhs if args.rhs > 0 else 8 * world) if pipelined else 1
     t0 = time.time()
     # pipelined mode: the two front solves of rank 0 (2 x 1.4 ms) weigh as much as ~330 strips (4.2 us per strip and sweep)
     S = distributed_gmres_setup(n, b, omega, w["const"], c_mat, rank, world, None, dev, front_equiv=330 if pipelined else 0)
