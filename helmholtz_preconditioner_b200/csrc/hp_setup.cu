@@ -8,6 +8,7 @@
 #include "hp_sweep4.h"
 
 #include <algorithm>
+#include <stdlib.h>
 
 struct HpSetupArgs {
     HpStripCtx c;
@@ -28,6 +29,7 @@ __device__ __forceinline__ cplx* hp_packet(const HpSetupArgs& a, int layer_in_ba
 }
 
 // thread -> (strip, leaf, direction)
+template <int BB>
 __global__ void __launch_bounds__(64) hp_chain_kernel(HpSetupArgs a) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int total = a.nb * a.lay.P * 2;
@@ -36,9 +38,168 @@ __global__ void __launch_bounds__(64) hp_chain_kernel(HpSetupArgs a) {
     int m = a.m0 + lb, n = a.c.n, bb = a.c.b * a.c.b;
     int i0 = a.leaf_start[l] + 1, i1 = a.leaf_start[l] + a.leaf_q[l];
     int bad;
-    if (dir == 0) bad = hp_chain_forward(a.Finv + (size_t)lb * n * bb, i0, i1, m, a.c);
-    else bad = hp_chain_backward(a.Binv + (size_t)lb * n * bb, a.gcol + (size_t)lb * n * a.c.b, i0, i1, m, a.c);
+    if (dir == 0) bad = hp_chain_forward<BB>(a.Finv + (size_t)lb * n * bb, i0, i1, m, a.c);
+    else bad = hp_chain_backward<BB>(a.Binv + (size_t)lb * n * bb, a.gcol + (size_t)lb * n * a.c.b, i0, i1, m, a.c);
     if (bad) atomicOr(a.status, 1);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Warp-cooperative Schur chains: warp -> (strip, leaf, direction), the b x b blocks live in shared memory and the
+// 32 lanes share every elimination step (the one-thread-per-chain kernel above keeps its blocks in local memory and
+// is bound by the L2 traffic of those spills: 2.2 s of the 3.2 s setup at 4096^2).  Same recurrences as
+// hp_chain_forward / hp_chain_backward (csrc/hp_setup_core.h), same operation order inside every entry.
+// ------------------------------------------------------------------------------------------------------
+struct HpLaneRow { cplx is2c, s2lo, s2hi; };                 // x2 factors of strip row k (lane k), cf. hp_strip_rows
+__device__ __forceinline__ HpLaneRow hp_lane_strip_row(int k, int m, int b, const HpPml& p) {
+    HpLaneRow R;
+    double shift = HP_MUL((double)(m - b), p.h);
+    int j = m - b + 1 + k;
+    R.is2c = hp_inv_s(hp_sigma2(HP_SUB(hp_coord(2 * j, p.h), shift), p), p);
+    R.s2lo = cinv(hp_inv_s(hp_sigma2(HP_SUB(hp_coord(2 * j - 1, p.h), shift), p), p));
+    R.s2hi = cinv(hp_inv_s(hp_sigma2(HP_SUB(hp_coord(2 * j + 1, p.h), shift), p), p));
+    return R;
+}
+// coefficients of block row i for strip row k (cf. hp_block_row): written to vec[0..5b) = L, U, sub, dia, sup
+__device__ __forceinline__ void hp_lane_block_row(cplx* vec, const HpLaneRow& R, int i, int k, int m, int b, const HpStripCtx& c) {
+    double ih2 = 1.0 / (c.pml.h * c.pml.h);
+    cplx s1lo = c.s1t[2 * i - 1], s1hi = c.s1t[2 * i + 1], is1c = c.is1t[2 * i];
+    int j = m - b + 1 + k;
+    cplx c1 = cscale(ih2, cmul(s1lo, R.is2c));
+    cplx c2 = cscale(ih2, cmul(s1hi, R.is2c));
+    cplx c3 = cscale(ih2, cmul(R.s2lo, is1c));
+    cplx c4 = cscale(ih2, cmul(R.s2hi, is1c));
+    double cv = c.c_mat[(size_t)(i - 1) * (c.n + 2) + (j - 1)];
+    cplx c5 = cscale(1.0 / (cv * cv), cmul(c.omega2, cmul(is1c, R.is2c)));
+    c5 = csub(c5, cadd(cadd(c1, c2), cadd(c3, c4)));
+    vec[k] = c1; vec[b + k] = c2; vec[2 * b + k] = c3; vec[3 * b + k] = c5; vec[4 * b + k] = c4;
+}
+// in-place Gauss-Jordan inverse with partial pivoting of the b x b matrix A in shared memory (b <= 32), one warp.
+// The pivot is the entry of largest modulus up to the lower 32 bits of the double (any such choice is stable).
+__device__ int hp_warp_inv(cplx* A, int b, int lane, int* piv) {
+    int bad = 0;
+    for (int p = 0; p < b; ++p) {
+        unsigned int key = 0u;
+        if (lane >= p && lane < b) {
+            double v = cabs2(A[lane * b + p]);
+            key = (unsigned int)(__double_as_longlong(v) >> 32) + (v > 0.0 ? 1u : 0u);   // monotone in v, 0 only for v == 0
+        }
+        unsigned int best = __reduce_max_sync(0xffffffffu, key);
+        if (best == 0u) bad = 1;
+        int r = __ffs(__ballot_sync(0xffffffffu, key == best && lane >= p && lane < b)) - 1;
+        if (r < 0) r = p;
+        if (lane == 0) piv[p] = r;
+        if (r != p && lane < b) { cplx t = A[p * b + lane]; A[p * b + lane] = A[r * b + lane]; A[r * b + lane] = t; }
+        __syncwarp();
+        cplx d = cinv(A[p * b + p]);
+        __syncwarp();
+        if (lane < b) A[p * b + lane] = cmul(lane == p ? cmake(1.0, 0.0) : A[p * b + lane], d);
+        __syncwarp();
+        // eliminate: every lane takes entries e = lane, lane+32, ... ; reads first, then writes
+        cplx nv[(HP_BMAX * HP_BMAX + 31) / 32];
+        int cnt = 0;
+        for (int e = lane; e < b * b; e += 32, ++cnt) {
+            int i = e / b, j = e - i * b;
+            cplx cur = A[e];
+            if (i != p) {
+                cplx f = A[i * b + p];
+                cur = cfms(f, A[p * b + j], j == p ? cmake(0.0, 0.0) : cur);
+            }
+            nv[cnt] = cur;
+        }
+        __syncwarp();
+        cnt = 0;
+        for (int e = lane; e < b * b; e += 32, ++cnt) A[e] = nv[cnt];
+        __syncwarp();
+    }
+    for (int p = b - 1; p >= 0; --p) {
+        int r = piv[p];
+        if (r != p && lane < b) { cplx t = A[lane * b + p]; A[lane * b + p] = A[lane * b + r]; A[lane * b + r] = t; }
+        __syncwarp();
+    }
+    return bad;
+}
+
+__global__ void __launch_bounds__(256) hp_chain_warp_kernel(HpSetupArgs a, int warps_per_block) {
+    extern __shared__ double2 smw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * warps_per_block + wib;
+    const int total = a.nb * a.lay.P * 2;
+    if (wib >= warps_per_block || warp >= total) return;
+    const int dir = warp & 1, l = (warp >> 1) % a.lay.P, lb = (warp >> 1) / a.lay.P;
+    const int m = a.m0 + lb, n = a.c.n, b = a.c.b, bb = b * b;
+    const int i0 = a.leaf_start[l] + 1, i1 = a.leaf_start[l] + a.leaf_q[l];
+    cplx* F = smw + (size_t)wib * (4 * bb + 6 * b + 16);      // F (then G), T1, T2, Bs, vec[5b], prev[b], piv
+    cplx* T1 = F + bb;
+    cplx* T2 = T1 + bb;
+    cplx* Bs = T2 + bb;
+    cplx* vec = Bs + bb;                                     // L, U, sub, dia, sup of the current block row
+    cplx* prev = vec + 5 * b;                                // U_{i-1} (forward) / L_{i+1} (backward)
+    int* piv = reinterpret_cast<int*>(prev + b);
+    HpLaneRow R;
+    if (lane < b) R = hp_lane_strip_row(lane, m, b, a.c.pml);
+    int bad = 0;
+    cplx* out = (dir == 0 ? a.Finv : a.Binv) + (size_t)lb * n * bb;
+    const int nsteps = i1 - i0 + 1;
+    for (int st = 0; st < nsteps; ++st) {
+        const int i = dir == 0 ? i0 + st : i1 - st;
+        if (lane < b) hp_lane_block_row(vec, R, i, lane, m, b, a.c);
+        __syncwarp();
+        // F = D_i - diag(a) Xinv diag(c):  forward a = L_i, c = U_{i-1};  backward a = U_i, c = L_{i+1}
+        const cplx* av = dir == 0 ? vec : vec + b;
+        for (int e = lane; e < bb; e += 32) {
+            int r = e / b, sc = e - r * b;
+            cplx v = cmake(0.0, 0.0);
+            if (r == sc) v = vec[3 * b + r];
+            else if (sc == r - 1) v = vec[2 * b + r];
+            else if (sc == r + 1) v = vec[4 * b + r];
+            if (st > 0) v = cfms(cmul(av[r], F[e]), prev[sc], v);
+            F[e] = v;
+        }
+        __syncwarp();
+        bad |= hp_warp_inv(F, b, lane, piv);
+        cplx* dst = out + (size_t)(i - 1) * bb;
+        for (int e = lane; e < bb; e += 32) dst[e] = F[e];
+        if (lane < b) prev[lane] = dir == 0 ? vec[b + lane] : vec[lane];
+        __syncwarp();
+    }
+    if (dir == 1) {
+        // diagonal blocks of the leaf inverse, ascending; F holds Binv[i0] = G_{i0,i0} now
+        cplx* G = F;
+        cplx* gcol = a.gcol + (size_t)lb * n * b;
+        for (int i = i0; i <= i1; ++i) {
+            if (lane < b) hp_lane_block_row(vec, R, i, lane, m, b, a.c);
+            __syncwarp();
+            if (i > i0) {
+                const cplx* Bi = out + (size_t)(i - 1) * bb;
+                for (int e = lane; e < bb; e += 32) {
+                    int r = e / b, sc = e - r * b;
+                    Bs[e] = Bi[e];
+                    T1[e] = cmul(cmul(vec[r], G[e]), prev[sc]);
+                }
+                __syncwarp();
+                for (int e = lane; e < bb; e += 32) {           // T2 = Bs T1
+                    int r = e / b, sc = e - r * b;
+                    cplx acc = cmake(0.0, 0.0);
+                    for (int t = 0; t < b; ++t) acc = cfma(Bs[r * b + t], T1[t * b + sc], acc);
+                    T2[e] = acc;
+                }
+                __syncwarp();
+                for (int e = lane; e < bb; e += 32) {           // G = Bs + T2 Bs
+                    int r = e / b, sc = e - r * b;
+                    cplx acc = Bs[e];
+                    for (int t = 0; t < b; ++t) acc = cfma(T2[r * b + t], Bs[t * b + sc], acc);
+                    G[e] = acc;
+                }
+                __syncwarp();
+            }
+            if (lane < b) {
+                gcol[(size_t)(i - 1) * b + lane] = G[lane * b + (b - 1)];
+                prev[lane] = vec[b + lane];
+            }
+            __syncwarp();
+        }
+    }
+    if (bad && lane == 0) atomicOr(a.status, 1);
 }
 
 // CTA -> (strip, leaf); thread -> leaf column r
@@ -89,6 +250,7 @@ __global__ void __launch_bounds__(128) hp_sep_blocks_kernel(HpSetupArgs a) {
 }
 
 // thread -> (strip, direction)
+template <int BB>
 __global__ void __launch_bounds__(32) hp_sep_chain_kernel(HpSetupArgs a) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int ns = a.lay.P - 1, bb = a.c.b * a.c.b;
@@ -96,18 +258,19 @@ __global__ void __launch_bounds__(32) hp_sep_chain_kernel(HpSetupArgs a) {
     int dir = t & 1, lb = t >> 1;
     size_t o = (size_t)lb * ns * bb;
     int bad;
-    if (dir == 0) bad = hp_sep_chain(a.FX + o, a.FXi + o, a.PF + o, a.Sd + o, a.So + o, ns, +1, a.c.b);
-    else bad = hp_sep_chain(a.BX + o, a.BXi + o, a.PB + o, a.Sd + o, a.So + o, ns, -1, a.c.b);
+    if (dir == 0) bad = hp_sep_chain<BB>(a.FX + o, a.FXi + o, a.PF + o, a.Sd + o, a.So + o, ns, +1, a.c.b);
+    else bad = hp_sep_chain<BB>(a.BX + o, a.BXi + o, a.PB + o, a.Sd + o, a.So + o, ns, -1, a.c.b);
     if (bad) atomicOr(a.status, 2);
 }
 
 // thread -> (strip, separator)
+template <int BB>
 __global__ void __launch_bounds__(64) hp_sep_diaginv_kernel(HpSetupArgs a) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int ns = a.lay.P - 1, bb = a.c.b * a.c.b;
     if (t >= a.nb * ns) return;
     size_t o = (size_t)t * bb;
-    if (hp_sep_diag_inverse(a.Njj + o, a.FX + o, a.BX + o, a.Sd + o, a.c.b)) atomicOr(a.status, 4);
+    if (hp_sep_diag_inverse<BB>(a.Njj + o, a.FX + o, a.BX + o, a.Sd + o, a.c.b)) atomicOr(a.status, 4);
 }
 
 // thread -> (strip, separator, component): one row of N (= column, N is symmetric).  Classic layout: written as a row
@@ -336,7 +499,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
                         (L.colN ? (size_t)L.NS * L.NSP : 0)) * sizeof(cplx);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    size_t cap = std::min<size_t>((size_t)(0.5 * (double)free_b), (size_t)12 << 30);
+    size_t cap = std::min<size_t>((size_t)(0.5 * (double)free_b), (size_t)64 << 30);   // many strips per batch: one thread per chain needs the parallelism
     int LB = (int)std::max<size_t>(1, std::min<size_t>((size_t)nstrips, cap / per_strip));
     HpSetupArgs a;
     a.c = hp_ctx(s); a.lay = L; a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
@@ -359,11 +522,23 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
     const int leaf_threads = ((L.QP + 31) / 32) * 32;
+    const bool small_b = b <= 12;                          // thread-local b x b matrices sized 144 instead of HP_BMAX^2
+    // warp-cooperative Schur chains: as many warps per block as fit in ~100 KB of shared memory (two blocks per SM)
+    const size_t chain_per_warp = sizeof(cplx) * ((size_t)4 * bb + 6 * b + 16);
+    int chain_wpb = (int)std::min<size_t>(8, (100 * 1024) / chain_per_warp);
+    if (getenv("HP_CHAIN_THREAD")) chain_wpb = 0;          // developer switch: the one-thread-per-chain kernel
+    const size_t chain_smem = chain_per_warp * (size_t)std::max(chain_wpb, 1);
+    if (chain_wpb > 0 && chain_smem > 48 * 1024)
+        HP_CUDA(cudaFuncSetAttribute(hp_chain_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem));
     for (int m0 = m_lo; m0 <= m_hi; m0 += LB) {
         a.m0 = m0;
         a.nb = std::min(LB, m_hi - m0 + 1);
         int t1 = a.nb * P * 2;
-        hp_count_launch(); hp_chain_kernel<<<(t1 + 63) / 64, 64, 0, st>>>(a);
+        hp_count_launch();
+        if (chain_wpb > 0) {
+            hp_chain_warp_kernel<<<(t1 + chain_wpb - 1) / chain_wpb, 32 * chain_wpb, chain_smem, st>>>(a, chain_wpb);
+        } else if (small_b) hp_chain_kernel<144><<<(t1 + 63) / 64, 64, 0, st>>>(a);
+        else hp_chain_kernel<HP_BMAX * HP_BMAX><<<(t1 + 63) / 64, 64, 0, st>>>(a);
         hp_count_launch(); hp_leaf_kernel<<<a.nb * P, leaf_threads, 0, st>>>(a);
         if (ns > 0) {
             if (P > 2) {
@@ -372,8 +547,10 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
             }
             int t4 = a.nb * ns;
             hp_count_launch(); hp_sep_blocks_kernel<<<(t4 + 127) / 128, 128, 0, st>>>(a);
-            hp_count_launch(); hp_sep_chain_kernel<<<(a.nb * 2 + 31) / 32, 32, 0, st>>>(a);
-            hp_count_launch(); hp_sep_diaginv_kernel<<<(t4 + 63) / 64, 64, 0, st>>>(a);
+            hp_count_launch();
+            if (small_b) hp_sep_chain_kernel<144><<<(a.nb * 2 + 31) / 32, 32, 0, st>>>(a); else hp_sep_chain_kernel<HP_BMAX * HP_BMAX><<<(a.nb * 2 + 31) / 32, 32, 0, st>>>(a);
+            hp_count_launch();
+            if (small_b) hp_sep_diaginv_kernel<144><<<(t4 + 63) / 64, 64, 0, st>>>(a); else hp_sep_diaginv_kernel<HP_BMAX * HP_BMAX><<<(t4 + 63) / 64, 64, 0, st>>>(a);
             int t7 = a.nb * ns * b;
             hp_count_launch(); hp_sep_rows_kernel<<<(t7 + 127) / 128, 128, 0, st>>>(a, rowbuf);
         }

@@ -11,6 +11,9 @@
 //   * the dense inverse N = S^{-1} of the separator Schur complement S (block tridiagonal, b x b blocks).
 // tools/strip_model.py is the numpy model of exactly these arrays.
 //
+// The functions that hold b x b matrices in thread-local arrays take the array size BB >= b*b as a template parameter
+// (144 for the reference's b = 12: a quarter of the local memory of the general HP_BMAX^2 case).
+//
 // Every function here is the body of ONE thread of a setup kernel (csrc/hp_setup.cu); the loops over
 // leaf columns are written so that the lanes of a warp walk the leaf in lock step and read the same
 // b x b matrix at the same time (broadcast loads).
@@ -28,13 +31,14 @@ struct HpStripCtx {
 
 // Forward Schur chain of one leaf: Finv[i] = (D_i - L_i Finv[i-1] U_{i-1})^{-1}, i = i0..i1 (1-based,
 // inclusive).  out points at this strip's [n][b*b] scratch.
+template <int BB = HP_BMAX * HP_BMAX>
 HP_HD int hp_chain_forward(cplx* out, int i0, int i1, int m, const HpStripCtx& c) {
     const int b = c.b, bb = b * b;
     HpStripRow R;
     hp_strip_rows(R, m, b, c.pml);
     HpBlockRow B;
     cplx Uprev[HP_BMAX];
-    cplx F[HP_BMAX * HP_BMAX];
+    cplx F[BB];
     int bad = 0;
     for (int i = i0; i <= i1; ++i) {
         hp_block_row(B, R, i, m, b, c.n, c.pml, c.s1t, c.is1t, c.c_mat, c.omega2);
@@ -51,13 +55,14 @@ HP_HD int hp_chain_forward(cplx* out, int i0, int i1, int m, const HpStripCtx& c
 // ascending recurrence for the diagonal blocks of the leaf inverse
 //   G_{i0,i0} = Binv[i0],   G_ii = Binv_i + Binv_i L_i G_{i-1,i-1} U_{i-1} Binv_i
 // of which only the last column (source in the last strip row) is kept: gcol[i][0..b).
+template <int BB = HP_BMAX * HP_BMAX>
 HP_HD int hp_chain_backward(cplx* out, cplx* gcol, int i0, int i1, int m, const HpStripCtx& c) {
     const int b = c.b, bb = b * b;
     HpStripRow R;
     hp_strip_rows(R, m, b, c.pml);
     HpBlockRow B;
     cplx Lnext[HP_BMAX];
-    cplx F[HP_BMAX * HP_BMAX];
+    cplx F[BB];
     int bad = 0;
     for (int i = i1; i >= i0; --i) {
         hp_block_row(B, R, i, m, b, c.n, c.pml, c.s1t, c.is1t, c.c_mat, c.omega2);
@@ -71,7 +76,7 @@ HP_HD int hp_chain_backward(cplx* out, cplx* gcol, int i0, int i1, int m, const 
     //   g_i = Binv_i e + Binv_i L_i G_{i-1,i-1} U_{i-1} Binv_i e   needs the full G_{i-1,i-1}, so the
     //   full block is carried in G.
     cplx* G = F;
-    cplx T1[HP_BMAX * HP_BMAX], T2[HP_BMAX * HP_BMAX];
+    cplx T1[BB], T2[BB];
     cplx Uprev[HP_BMAX];
     for (int i = i0; i <= i1; ++i) {
         const cplx* Bi = out + (size_t)(i - 1) * bb;
@@ -214,9 +219,10 @@ HP_HD void hp_sep_offdiag(cplx* So, int s, int s2, int m, const cplx* tp, const 
 //   bwd: X_j = S_jj - S_{j,j+1} Xinv_{j+1} S_{j+1,j},  Xinv_j,  Prop_j = -Xinv_j S_{j,j-1}
 // Sd [ns][b*b], So [ns-1][b*b] (So[j] = S_{j,j+1}; S_{j+1,j} is its transpose).
 // X, Xinv, Prop: [ns][b*b] each.
+template <int BB = HP_BMAX * HP_BMAX>
 HP_HD int hp_sep_chain(cplx* X, cplx* Xinv, cplx* Prop, const cplx* Sd, const cplx* So, int ns, int dir, int b) {
     const int bb = b * b;
-    cplx F[HP_BMAX * HP_BMAX], T1[HP_BMAX * HP_BMAX], A[HP_BMAX * HP_BMAX];
+    cplx F[BB], T1[BB], A[BB];
     int bad = 0;
     for (int step = 0; step < ns; ++step) {
         int j = dir > 0 ? step : ns - 1 - step;
@@ -252,8 +258,9 @@ HP_HD int hp_sep_chain(cplx* X, cplx* Xinv, cplx* Prop, const cplx* Sd, const cp
 }
 
 // N_jj = (FX_j + BX_j - S_jj)^{-1}
+template <int BB = HP_BMAX * HP_BMAX>
 HP_HD int hp_sep_diag_inverse(cplx* Njj, const cplx* FX, const cplx* BX, const cplx* Sd, int b) {
-    cplx F[HP_BMAX * HP_BMAX];
+    cplx F[BB];
     for (int e = 0; e < b * b; ++e) F[e] = csub(cadd(FX[e], BX[e]), Sd[e]);
     int bad = hp_inv_inplace(F, b);
     for (int e = 0; e < b * b; ++e) Njj[e] = F[e];
