@@ -214,8 +214,8 @@ def bench_distributed(args, w, make_fields, config_dict, ClockSampler):
     pipelined = args.mp_mode == "pipelined"
     R = (args.rhs if args.rhs > 0 else 8 * world) if pipelined else 1
     t0 = time.time()
-    # pipelined mode: the two front solves of rank 0 (2 x 1.4 ms) weigh as much as ~330 strips (4.2 us per strip and sweep)
-    S = distributed_gmres_setup(n, b, omega, w["const"], c_mat, rank, world, None, dev, front_equiv=330 if pipelined else 0)
+    # (the front solves of rank 0 are parallel scans of ~10 us: no re-balancing of the slabs needed, front_equiv = 0)
+    S = distributed_gmres_setup(n, b, omega, w["const"], c_mat, rank, world, None, dev)
     torch.cuda.synchronize()
     t_setup = time.time() - t0
     # right-hand sides: the source of the reference moved along x1 (one shot position per right-hand side)
