@@ -64,27 +64,44 @@ __device__ __forceinline__ HpPointCoef hp_point_coef(int i, int j, int n, double
 
 // One thread per matrix row.  Row r = (j-1) n + (i-1) stores, in ascending column order, the couplings
 // to (i, j-1), (i-1, j), itself, (i+1, j), (i, j+1); neighbours outside the grid are dropped.  The row
-// offset has a closed form, so indptr needs no scan.
-__global__ void __launch_bounds__(256) hp_assemble_csr_kernel(int n, double ih2, cplx omega2,
+// offset has a closed form, so indptr needs no scan.  The rows of a CTA are consecutive, hence so are their
+// entries: they are assembled in shared memory and written out with consecutive threads on consecutive entries
+// (a thread writing its own 3-5 entries would touch every 32-byte sector five times).
+#define HP_ASM_THREADS 256
+__device__ __forceinline__ int64_t hp_csr_row_offset(int64_t r, int64_t nn) {
+    const int64_t j0 = r / nn, i0 = r - j0 * nn;
+    return 5 * r - (r < nn ? r : nn) - (r > (nn - 1) * nn ? r - (nn - 1) * nn : 0) - (j0 + (i0 > 0 ? 1 : 0)) - j0;
+}
+__global__ void __launch_bounds__(HP_ASM_THREADS) hp_assemble_csr_kernel(int n, double ih2, cplx omega2,
         const cplx* __restrict__ s1t, const cplx* __restrict__ is1t, const cplx* __restrict__ s2t,
         const cplx* __restrict__ is2t, const double* __restrict__ kappa,
         int32_t* __restrict__ indptr, int32_t* __restrict__ indices, cplx* __restrict__ data) {
-    int64_t N = (int64_t)n * n;
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= N) return;
-    int j0 = (int)(r / n), i0 = (int)(r % n);
-    int64_t nn = n;
-    int64_t off = 5 * r - (r < nn ? r : nn) - (r > (nn - 1) * nn ? r - (nn - 1) * nn : 0)
-                  - (j0 + (i0 > 0 ? 1 : 0)) - j0;
-    HpPointCoef c = hp_point_coef(i0 + 1, j0 + 1, n, ih2, omega2, s1t, is1t, s2t, is2t, kappa[r]);
-    indptr[r] = (int32_t)off;
-    int64_t o = off;
-    if (j0 > 0)     { indices[o] = (int32_t)(r - n); data[o] = c.c3; ++o; }
-    if (i0 > 0)     { indices[o] = (int32_t)(r - 1); data[o] = c.c1; ++o; }
-                      indices[o] = (int32_t)r;       data[o] = c.c5; ++o;
-    if (i0 < n - 1) { indices[o] = (int32_t)(r + 1); data[o] = c.c2; ++o; }
-    if (j0 < n - 1) { indices[o] = (int32_t)(r + n); data[o] = c.c4; ++o; }
-    if (r == N - 1) indptr[N] = (int32_t)o;
+    __shared__ cplx sdata[HP_ASM_THREADS * 5];
+    __shared__ int32_t sidx[HP_ASM_THREADS * 5];
+    const int64_t N = (int64_t)n * n, nn = n;
+    const int64_t r0 = (int64_t)blockIdx.x * HP_ASM_THREADS, r = r0 + threadIdx.x;
+    const int64_t rend = r0 + HP_ASM_THREADS < N ? r0 + HP_ASM_THREADS : N;
+    const int64_t off0 = hp_csr_row_offset(r0, nn);
+    const int64_t off1 = rend < N ? hp_csr_row_offset(rend, nn) : 5 * N - 4 * nn;
+    if (r < N) {
+        const int j0 = (int)(r / n), i0 = (int)(r % n);
+        const int64_t off = hp_csr_row_offset(r, nn);
+        HpPointCoef c = hp_point_coef(i0 + 1, j0 + 1, n, ih2, omega2, s1t, is1t, s2t, is2t, kappa[r]);
+        indptr[r] = (int32_t)off;
+        int o = (int)(off - off0);
+        if (j0 > 0)     { sidx[o] = (int32_t)(r - n); sdata[o] = c.c3; ++o; }
+        if (i0 > 0)     { sidx[o] = (int32_t)(r - 1); sdata[o] = c.c1; ++o; }
+                          sidx[o] = (int32_t)r;       sdata[o] = c.c5; ++o;
+        if (i0 < n - 1) { sidx[o] = (int32_t)(r + 1); sdata[o] = c.c2; ++o; }
+        if (j0 < n - 1) { sidx[o] = (int32_t)(r + n); sdata[o] = c.c4; ++o; }
+        if (r == N - 1) indptr[N] = (int32_t)(off0 + o);
+    }
+    __syncthreads();
+    const int cnt = (int)(off1 - off0);
+    for (int e = threadIdx.x; e < cnt; e += HP_ASM_THREADS) {
+        data[off0 + e] = sdata[e];
+        indices[off0 + e] = sidx[e];
+    }
 }
 
 // Matrix-free y = A x.  A CTA owns 128 consecutive x1 columns and marches over HP_SPMV_ROWS grid rows;
@@ -168,7 +185,7 @@ extern "C" int hp_assemble_csr(hp_solver* s, int32_t* indptr, int32_t* indices, 
     if (hp_csr_nnz(s->n) > 2147483647LL) { hp_set_error("hp_assemble_csr: nnz exceeds int32 indices"); return 1; }
     int64_t N = (int64_t)s->n * s->n;
     double ih2 = 1.0 / (s->pml.h * s->pml.h);
-    hp_count_launch(); hp_assemble_csr_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    hp_count_launch(); hp_assemble_csr_kernel<<<(unsigned)((N + HP_ASM_THREADS - 1) / HP_ASM_THREADS), HP_ASM_THREADS, 0, (cudaStream_t)stream>>>(
         s->n, ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa, indptr, indices, (cplx*)data);
     HP_CUDA(cudaGetLastError());
     return 0;
