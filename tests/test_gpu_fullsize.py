@@ -157,3 +157,33 @@ def test_run_solver_127_vs_oracle(hp, diag):
     assert np.allclose(r.residuals[:k], hist0[:k], rtol=1e-7)
     if r.niter == niter0:
         assert rel(r.u, u0) < 1e-8
+
+
+@pytest.mark.parametrize("n,b", [(6000, 12), (3000, 20)])
+def test_wide_parts_cluster_vs_classic(hp, n, b):
+    """Parts wider than 32 columns (one lane per column, several W chunks per strip) and the generic (b, K)
+    instantiation of the cluster kernel: a sub-range of strips against SuperLU and against the classic layout."""
+    import scipy.sparse.linalg as spla
+    omega = 2 * np.pi * n / 10 + 2j
+    h = 1 / (n + 1)
+    c_mat, _ = hp.init_layered_f1(omega, n)
+    m_lo, m_hi = n // 2, n // 2 + 60
+    u0 = rnd(n * n, 9)
+    res = {}
+    for layout in ("cluster", "classic"):
+        s = hp.HelmholtzSolver(n, b, omega, 100.0, c_mat).setup_preconditioner(m_lo=m_lo, m_hi=m_hi, layout=layout)
+        assert s.layout()["colN"] == (layout == "cluster")
+        u = u0.clone()
+        s.sweep_forward(u, m_lo, m_hi - 1)
+        s.sweep_backward(u, m_hi, m_lo, "paper")
+        s.sweep_backward(u, m_hi, m_lo, "reference")
+        res[layout] = u[(m_lo - 2) * n:(m_hi + 1) * n].clone()
+        if layout == "cluster":
+            v = rnd(n, 10)
+            lu = spla.splu(orc.get_Hm(m_hi, b, 100.0, b * h, omega, h, n, c_mat).tocsc())
+            t = np.zeros(b * n, complex)
+            t[-n:] = v.cpu().numpy()
+            assert rel(s.strip_apply(m_hi, v), lu.solve(t)[-n:]) < 1e-11
+        assert s.sweep_status() == 0
+        s.close()
+    assert rel(res["cluster"], res["classic"]) < 1e-10
