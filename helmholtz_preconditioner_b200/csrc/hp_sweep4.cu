@@ -60,15 +60,22 @@ __device__ __forceinline__ bool mbar_try_cluster(unsigned long long* bar, unsign
         "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// bounded wait: a runaway wait (a bug) marks the CTA dead, all later waits fall through and the kernel terminates
-__device__ __forceinline__ void mbar_wait4(unsigned long long* bar, unsigned int parity, unsigned int* abort_flag,
-                                           volatile unsigned int* dead) {
+// bounded wait: a runaway wait (a bug) marks the CTA dead, all later waits fall through and the kernel terminates.
+// The spin loop is kept out of line: ~20 wait sites would otherwise carry a 4x unrolled copy each (a third of the
+// kernel's instructions), and the hot path of a wait is a single try_wait.
+__device__ __noinline__ void mbar_wait4_slow(unsigned long long* bar, unsigned int parity, unsigned int* abort_flag,
+                                             volatile unsigned int* dead) {
     unsigned int spins = 0;
+#pragma unroll 1
     while (!mbar_try_cluster(bar, parity)) {
         if (*dead) break;
         if (++spins > (1u << 20)) { atomicExch(abort_flag, 1u); *dead = 1u; break; }
         if ((spins & 0x3FF) == 0 && *((volatile unsigned int*)abort_flag)) { *dead = 1u; break; }
     }
+}
+__device__ __forceinline__ void mbar_wait4(unsigned long long* bar, unsigned int parity, unsigned int* abort_flag,
+                                           volatile unsigned int* dead) {
+    if (!mbar_try_cluster(bar, parity)) mbar_wait4_slow(bar, parity, abort_flag, dead);
 }
 __device__ __forceinline__ void mbar_arrive_local(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
