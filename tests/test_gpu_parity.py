@@ -209,3 +209,27 @@ def test_medium_preconditioner_vs_oracle(hp, layout):
         assert relerr(hp.algo2_4(f, b, n, s, diag="paper"), Pc_paper) < 1e-12
     assert s.sweep_status() == 0
     s.close()
+
+
+@pytest.mark.parametrize("nstrips", [1, 2, 3, 4, 5, 7])
+def test_short_sweeps_cluster_vs_classic(hp, nstrips):
+    """Sweeps over very few strips (ring prologues / epilogues of the pipelined kernels): cluster layout against
+    the classic layout on the same strip range, forward and both backward variants."""
+    n, b = 200, 12
+    omega = 2 * np.pi * (n / 10) + 2j
+    c_mat = orc.init_c1_f1(omega, n)[0]
+    rng = np.random.default_rng(21)
+    u0 = dev(rng.standard_normal(n * n) + 1j * rng.standard_normal(n * n))
+    m_lo = 60
+    m_hi = m_lo + nstrips - 1
+    res = {}
+    for layout in ("cluster", "classic"):
+        s = hp.HelmholtzSolver(n, b, omega, 60.0, c_mat).setup_preconditioner(m_lo=m_lo, m_hi=m_hi, layout=layout)
+        u = u0.clone()
+        s.sweep_forward(u, m_lo, m_hi)
+        s.sweep_backward(u, m_hi, m_lo, "reference")
+        s.sweep_backward(u, m_hi, m_lo, "paper")
+        res[layout] = u.clone()
+        assert s.sweep_status() == 0
+        s.close()
+    assert relerr(res["cluster"], res["classic"].cpu().numpy()) < 1e-12
