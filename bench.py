@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="interior grid points per side (default: 4096 at N=1)")
+    ap.add_argument("--n", "--grid-n", dest="n", type=int, default=0, help="interior grid points per side (default: 4096; --grid-n under torchrun, whose parser claims --n)")
     ap.add_argument("--b", type=int, default=12, help="PML width in grid points (reference: 12)")
     ap.add_argument("--ppw", type=float, default=10.0, help="grid points per wavelength")
     ap.add_argument("--const", type=float, default=100.0)
