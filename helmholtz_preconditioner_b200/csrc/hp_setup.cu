@@ -202,6 +202,208 @@ __global__ void __launch_bounds__(256) hp_chain_warp_kernel(HpSetupArgs a, int w
     if (bad && lane == 0) atomicOr(a.status, 1);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Register-resident Schur chains (compile-time b): one warp runs BOTH chains of a leaf, lanes 0-15 the forward
+// chain, lanes 16-31 the backward one.  Lane j < B of a half keeps column j of the b x b block in registers, so a
+// Gauss-Jordan step is a local pivot search in lane p, one broadcast of the pivot and of the B-1 multipliers
+// (width-16 shuffles) and B-1 fused multiply-subtracts per lane; nothing of the block goes through shared memory.
+// The coefficients of a block row factor into an x1 part (tables) and the x2 part of the strip row, so the
+// Schur update F = D_i - diag(a) X diag(c) needs no exchange either.  The ascending recurrence of the backward
+// chain (two b x b products per block row) is shared by both halves, operands broadcast from shared memory.
+// Same recurrences and the same operation order inside every entry as hp_chain_warp_kernel; the shared-memory
+// kernel spent its time on instruction issue (index arithmetic, shared-memory round trips, 6 warp syncs per pivot).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ cplx hp_shfl16(cplx v, int src) {
+    return cmake(__shfl_sync(0xffffffffu, v.x, src, 16), __shfl_sync(0xffffffffu, v.y, src, 16));
+}
+
+// in-place inverse of the B x B matrix whose column j is A[0..B) of lane j of each half-warp (partial pivoting)
+template <int B>
+__device__ __forceinline__ int hp_half_inv(cplx (&A)[B], int j) {
+    int bad = 0;
+    int piv[B];
+#pragma unroll
+    for (int p = 0; p < B; ++p) {
+        // pivot search: lane p holds column p
+        int r_own = p;
+        double best = cabs2(A[p]);
+#pragma unroll
+        for (int i = p + 1; i < B; ++i) {
+            const double v = cabs2(A[i]);
+            if (v > best) { best = v; r_own = i; }
+        }
+        const int r = __shfl_sync(0xffffffffu, r_own, p, 16);
+        if (__shfl_sync(0xffffffffu, best, p, 16) == 0.0) bad = 1;
+        piv[p] = r;
+#pragma unroll
+        for (int i = p + 1; i < B; ++i)
+            if (i == r) { const cplx t = A[i]; A[i] = A[p]; A[p] = t; }
+        const cplx d = cinv(hp_shfl16(A[p], p));
+        const cplx prow = cmul(j == p ? cmake(1.0, 0.0) : A[p], d);
+        A[p] = prow;
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+            if (i == p) continue;
+            const cplx f = hp_shfl16(A[i], p);
+            A[i] = cfms(f, prow, j == p ? cmake(0.0, 0.0) : A[i]);
+        }
+    }
+    // undo the row exchanges on the columns (columns live in lanes)
+#pragma unroll
+    for (int p = B - 1; p >= 0; --p) {
+        const int r = piv[p];
+        if (__any_sync(0xffffffffu, r != p)) {
+            const int src = j == p ? r : (j == r ? p : j);
+#pragma unroll
+            for (int i = 0; i < B; ++i) A[i] = hp_shfl16(A[i], src);
+        }
+    }
+    return bad;
+}
+
+template <int B>
+__global__ void __launch_bounds__(128) hp_chain_reg_kernel(HpSetupArgs a) {
+    constexpr int BBc = B * B, RH = (B + 1) / 2;
+    __shared__ cplx s_tab[4][B];                 // 1/s2 at the strip rows (both halves work on the same strip)
+    __shared__ cplx s_mat[4][3][BBc];            // ascending pass: Binv_i, T2, G (row major)
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int pair = blockIdx.x * 4 + wib;
+    if (pair >= a.nb * a.lay.P) return;
+    const int h = lane >> 4, j = lane & 15;
+    const bool act = j < B;
+    const int jc = act ? j : B - 1;
+    const int l = pair % a.lay.P, lb = pair / a.lay.P;
+    const int m = a.m0 + lb, n = a.c.n;
+    const int i0 = a.leaf_start[l] + 1, i1 = a.leaf_start[l] + a.leaf_q[l], nsteps = i1 - i0 + 1;
+    const double ih2 = 1.0 / (a.c.pml.h * a.c.pml.h);
+    const HpLaneRow Rj = hp_lane_strip_row(jc, m, B, a.c.pml);
+    const cplx s2lo_n = hp_shfl16(Rj.s2lo, min(j + 1, 15));        // strip row j+1
+    const cplx s2hi_p = hp_shfl16(Rj.s2hi, max(j - 1, 0));         // strip row j-1
+    if (h == 0 && act) s_tab[wib][j] = Rj.is2c;
+    __syncwarp();
+    const cplx* tab = s_tab[wib];
+    const int jg = m - B + 1 + jc;                                 // grid row of strip row j
+    // coefficients of block row i at strip row j (cf. hp_lane_block_row): c1 = L, c2 = U, dia
+    auto coeffs = [&](int i, cplx& c1, cplx& c2, cplx& dia, cplx& is1c) {
+        const cplx s1lo = a.c.s1t[2 * i - 1], s1hi = a.c.s1t[2 * i + 1];
+        is1c = a.c.is1t[2 * i];
+        c1 = cscale(ih2, cmul(s1lo, Rj.is2c));
+        c2 = cscale(ih2, cmul(s1hi, Rj.is2c));
+        const cplx c3 = cscale(ih2, cmul(Rj.s2lo, is1c));
+        const cplx c4 = cscale(ih2, cmul(Rj.s2hi, is1c));
+        const double cv = a.c.c_mat[(size_t)(i - 1) * (n + 2) + (jg - 1)];
+        const cplx c5 = cscale(1.0 / (cv * cv), cmul(a.c.omega2, cmul(is1c, Rj.is2c)));
+        dia = csub(c5, cadd(cadd(c1, c2), cadd(c3, c4)));
+    };
+
+    cplx A[B];
+#pragma unroll
+    for (int r = 0; r < B; ++r) A[r] = cmake(0.0, 0.0);
+    cplx prevj = cmake(0.0, 0.0);                                  // U_{i-1}[j] (forward) / L_{i+1}[j] (backward)
+    int bad = 0;
+    cplx* out = (h == 0 ? a.Finv : a.Binv) + (size_t)lb * n * BBc;
+    for (int st = 0; st < nsteps; ++st) {
+        const int i = h == 0 ? i0 + st : i1 - st;
+        cplx c1, c2, dia, is1c;
+        coeffs(i, c1, c2, dia, is1c);
+        const cplx s1a = h == 0 ? a.c.s1t[2 * i - 1] : a.c.s1t[2 * i + 1];     // a_r = L_i[r] (forward) / U_i[r] (backward)
+        const cplx subn = cscale(ih2, cmul(s2lo_n, is1c));                     // D[j+1][j]
+        const cplx supp = cscale(ih2, cmul(s2hi_p, is1c));                     // D[j-1][j]
+#pragma unroll
+        for (int r = 0; r < B; ++r) {
+            cplx v = cmake(0.0, 0.0);
+            if (r == j) v = dia;
+            else if (r == j + 1) v = subn;
+            else if (r == j - 1) v = supp;
+            if (st > 0) {
+                const cplx av = cscale(ih2, cmul(s1a, tab[r]));
+                v = cfms(cmul(av, A[r]), prevj, v);
+            }
+            A[r] = v;
+        }
+        if (!act) {                                                // idle lanes carry a zero column
+#pragma unroll
+            for (int r = 0; r < B; ++r) A[r] = cmake(0.0, 0.0);
+        }
+        bad |= hp_half_inv<B>(A, j);
+        if (act) {
+            cplx* dst = out + (size_t)(i - 1) * BBc + j;
+#pragma unroll
+            for (int r = 0; r < B; ++r) dst[r * B] = A[r];
+        }
+        prevj = h == 0 ? c2 : c1;
+    }
+    // ---- diagonal blocks of the leaf inverse, ascending (backward chain; both halves share the products):
+    //      lane (h, j) forms rows h*RH .. of column j.  G starts as Binv[i0], held by the backward half.
+    cplx* Bs = s_mat[wib][0];
+    cplx* T2s = s_mat[wib][1];
+    cplx* Gs = s_mat[wib][2];
+    cplx* gcol = a.gcol + (size_t)lb * n * B;
+    const cplx* binv = a.Binv + (size_t)lb * n * BBc;
+    if (h == 1 && act) {
+#pragma unroll
+        for (int r = 0; r < B; ++r) Gs[r * B + j] = A[r];
+        if (j == B - 1)
+            for (int r = 0; r < B; ++r) gcol[(size_t)(i0 - 1) * B + r] = A[r];
+    }
+    {   // U_{i0}[j]
+        cplx c1, c2, dia, is1c;
+        coeffs(i0, c1, c2, dia, is1c);
+        prevj = c2;
+    }
+    __syncwarp();
+    const int r0 = h * RH, r1 = min(B, r0 + RH);
+    for (int i = i0 + 1; i <= i1; ++i) {
+        cplx c1, c2, dia, is1c;
+        coeffs(i, c1, c2, dia, is1c);
+        const cplx s1lo = a.c.s1t[2 * i - 1];
+        cplx Bcol[B], T1[B];
+        if (act) {
+            const cplx* Bi = binv + (size_t)(i - 1) * BBc + j;
+#pragma unroll
+            for (int t = 0; t < B; ++t) Bcol[t] = __ldcg(reinterpret_cast<const double2*>(Bi + t * B));
+#pragma unroll
+            for (int t = 0; t < B; ++t) {
+                const cplx Lt = cscale(ih2, cmul(s1lo, tab[t]));
+                T1[t] = cmul(cmul(Lt, Gs[t * B + j]), prevj);
+            }
+#pragma unroll
+            for (int t = 0; t < B; ++t)
+                if (t >= r0 && t < r1) Bs[t * B + j] = Bcol[t];
+        }
+        __syncwarp();
+        if (act) {
+#pragma unroll
+            for (int rr = 0; rr < RH; ++rr) {
+                const int r = r0 + rr;
+                if (r < r1) {
+                    cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+                    for (int t = 0; t < B; ++t) acc = cfma(Bs[r * B + t], T1[t], acc);
+                    T2s[r * B + j] = acc;
+                }
+            }
+        }
+        __syncwarp();
+        if (act) {
+#pragma unroll
+            for (int rr = 0; rr < RH; ++rr) {
+                const int r = r0 + rr;
+                if (r < r1) {
+                    cplx acc = Bs[r * B + j];
+#pragma unroll
+                    for (int t = 0; t < B; ++t) acc = cfma(T2s[r * B + t], Bcol[t], acc);
+                    Gs[r * B + j] = acc;
+                    if (j == B - 1) gcol[(size_t)(i - 1) * B + r] = acc;
+                }
+            }
+        }
+        prevj = c2;
+        __syncwarp();
+    }
+    if (bad && lane == 0) atomicOr(a.status, 1);
+}
+
 // CTA -> (strip, leaf); thread -> leaf column r
 __global__ void hp_leaf_kernel(HpSetupArgs a) {
     int l = blockIdx.x % a.lay.P, lb = blockIdx.x / a.lay.P;
@@ -623,7 +825,9 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
         a.nb = std::min(LB, m_hi - m0 + 1);
         int t1 = a.nb * P * 2;
         hp_count_launch();
-        if (chain_wpb > 0) {
+        if (chain_wpb > 0 && b == 12 && !getenv("HP_CHAIN_SMEM")) {
+            hp_chain_reg_kernel<12><<<(a.nb * P + 3) / 4, 128, 0, st>>>(a);        // one warp per leaf: both chains
+        } else if (chain_wpb > 0) {
             hp_chain_warp_kernel<<<(t1 + chain_wpb - 1) / chain_wpb, 32 * chain_wpb, chain_smem, st>>>(a, chain_wpb);
         } else if (small_b) hp_chain_kernel<144><<<(t1 + 63) / 64, 64, 0, st>>>(a);
         else hp_chain_kernel<HP_BMAX * HP_BMAX><<<(t1 + 63) / 64, 64, 0, st>>>(a);

@@ -62,7 +62,9 @@ else:
             s.lib.hp_debug_phases(s.handle, 0, raw.ctypes.data)
             out = raw[:L["G"] * 16].reshape(L["G"], 16)
             os.makedirs("gpurun_out", exist_ok=True)
-            np.save("gpurun_out/timeline4.npy", raw[L["G"] * 16:L["G"] * (16 + 1024)].reshape(L["G"], 64, 16))
+            tag = os.environ.get("HP_TAG", "")
+            np.save(f"gpurun_out/timeline4{tag}.npy", raw[L["G"] * 16:L["G"] * (16 + 1024)].reshape(L["G"], 64, 16))
+            np.save(f"gpurun_out/phases4{tag}.npy", out)
             nst = n - 1 - b
             names = ["pre (GL,GF,R)", "A wait x3", "B rho+bar", "C rows", "D poll", "D sum+send", "-", "-",
                      "a G wait", "a gb", "b wait x3", "b corr+send", "c wait V", "c W", "c tail", "(W chunk waits)"]
