@@ -17,6 +17,7 @@ struct HpSetupArgs {
     int m0;            // first strip of this batch
     int nb;            // strips in this batch
     int m_lo;          // first strip of the solver (packet index origin)
+    int leaf_piped;    // leaf kernel: propagators prefetched through registers (developer switch HP_LEAF_NOPIPE)
     cplx *Finv, *Binv, *gcol;             // [nb][n][bb], [nb][n][bb], [nb][n][b]
     cplx* tp;                             // [nb][P][bb]
     cplx *Sd, *So, *FX, *FXi, *PF, *BX, *BXi, *PB, *Njj;   // [nb][max(ns,1)][bb]
@@ -217,41 +218,87 @@ __device__ __forceinline__ cplx hp_shfl16(cplx v, int src) {
     return cmake(__shfl_sync(0xffffffffu, v.x, src, 16), __shfl_sync(0xffffffffu, v.y, src, 16));
 }
 
-// in-place inverse of the B x B matrix whose column j is A[0..B) of lane j of each half-warp (partial pivoting)
-template <int B>
+// in-place inverse of the B x B matrix whose column j is A[0..B) of lane j of each half-warp (partial pivoting).
+// The pivot loop is NOT unrolled (unrolled, the kernel is ~90 KB of straight-line code and stalls on instruction
+// fetch): after every step the rows are rotated by one register, so that the pivot row is always A[0] and the
+// body is the same code for every p; after B steps the rows are back in place.  Pivot rows are kept as 4-bit
+// fields of one 64-bit word.
+template <int B, bool ROLL = true>
 __device__ __forceinline__ int hp_half_inv(cplx (&A)[B], int j) {
+    static_assert(B <= 16, "pivot indices are packed in 4 bits");
     int bad = 0;
-    int piv[B];
+    unsigned long long pivs = 0ull;
+    if (!ROLL) {                                     // developer variant: fully unrolled pivot loop
+        int piv[B];
 #pragma unroll
+        for (int p = 0; p < B; ++p) {
+            int r_own = p;
+            double best = cabs2(A[p]);
+#pragma unroll
+            for (int i = p + 1; i < B; ++i) {
+                const double v = cabs2(A[i]);
+                if (v > best) { best = v; r_own = i; }
+            }
+            const int r = __shfl_sync(0xffffffffu, r_own, p, 16);
+            if (__shfl_sync(0xffffffffu, best, p, 16) == 0.0) bad = 1;
+            piv[p] = r;
+#pragma unroll
+            for (int i = p + 1; i < B; ++i)
+                if (i == r) { const cplx t = A[i]; A[i] = A[p]; A[p] = t; }
+            const cplx d = cinv(hp_shfl16(A[p], p));
+            const cplx prow = cmul(j == p ? cmake(1.0, 0.0) : A[p], d);
+            A[p] = prow;
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                if (i == p) continue;
+                const cplx f = hp_shfl16(A[i], p);
+                A[i] = cfms(f, prow, j == p ? cmake(0.0, 0.0) : A[i]);
+            }
+        }
+#pragma unroll
+        for (int p = B - 1; p >= 0; --p) {
+            const int r = piv[p];
+            if (__any_sync(0xffffffffu, r != p)) {
+                const int src = j == p ? r : (j == r ? p : j);
+#pragma unroll
+                for (int i = 0; i < B; ++i) A[i] = hp_shfl16(A[i], src);
+            }
+        }
+        return bad;
+    }
+#pragma unroll 1
     for (int p = 0; p < B; ++p) {
-        // pivot search: lane p holds column p
-        int r_own = p;
-        double best = cabs2(A[p]);
+        // logical row i >= p sits in A[i - p]; pivot search in lane p, which holds column p
+        int k_own = 0;
+        double best = cabs2(A[0]);
 #pragma unroll
-        for (int i = p + 1; i < B; ++i) {
-            const double v = cabs2(A[i]);
-            if (v > best) { best = v; r_own = i; }
+        for (int k = 1; k < B; ++k) {
+            const double v = cabs2(A[k]);
+            if (k < B - p && v > best) { best = v; k_own = k; }
         }
-        const int r = __shfl_sync(0xffffffffu, r_own, p, 16);
+        const int kr = __shfl_sync(0xffffffffu, k_own, p, 16);
         if (__shfl_sync(0xffffffffu, best, p, 16) == 0.0) bad = 1;
-        piv[p] = r;
+        pivs |= (unsigned long long)(p + kr) << (4 * p);
+        if (__any_sync(0xffffffffu, kr != 0)) {
 #pragma unroll
-        for (int i = p + 1; i < B; ++i)
-            if (i == r) { const cplx t = A[i]; A[i] = A[p]; A[p] = t; }
-        const cplx d = cinv(hp_shfl16(A[p], p));
-        const cplx prow = cmul(j == p ? cmake(1.0, 0.0) : A[p], d);
-        A[p] = prow;
-#pragma unroll
-        for (int i = 0; i < B; ++i) {
-            if (i == p) continue;
-            const cplx f = hp_shfl16(A[i], p);
-            A[i] = cfms(f, prow, j == p ? cmake(0.0, 0.0) : A[i]);
+            for (int k = 1; k < B; ++k)
+                if (k == kr) { const cplx t = A[k]; A[k] = A[0]; A[0] = t; }
         }
+        const cplx d = cinv(hp_shfl16(A[0], p));
+        const bool isp = j == p;
+        const cplx prow = cmul(isp ? cmake(1.0, 0.0) : A[0], d);
+        // eliminate the other rows and rotate: new A[k-1] = updated A[k], new A[B-1] = pivot row
+#pragma unroll
+        for (int k = 1; k < B; ++k) {
+            const cplx f = hp_shfl16(A[k], p);
+            A[k - 1] = cfms(f, prow, isp ? cmake(0.0, 0.0) : A[k]);
+        }
+        A[B - 1] = prow;
     }
     // undo the row exchanges on the columns (columns live in lanes)
-#pragma unroll
+#pragma unroll 1
     for (int p = B - 1; p >= 0; --p) {
-        const int r = piv[p];
+        const int r = (int)((pivs >> (4 * p)) & 15ull);
         if (__any_sync(0xffffffffu, r != p)) {
             const int src = j == p ? r : (j == r ? p : j);
 #pragma unroll
@@ -261,7 +308,7 @@ __device__ __forceinline__ int hp_half_inv(cplx (&A)[B], int j) {
     return bad;
 }
 
-template <int B>
+template <int B, bool ROLL>
 __global__ void __launch_bounds__(128) hp_chain_reg_kernel(HpSetupArgs a) {
     constexpr int BBc = B * B, RH = (B + 1) / 2;
     __shared__ cplx s_tab[4][B];                 // 1/s2 at the strip rows (both halves work on the same strip)
@@ -325,7 +372,7 @@ __global__ void __launch_bounds__(128) hp_chain_reg_kernel(HpSetupArgs a) {
 #pragma unroll
             for (int r = 0; r < B; ++r) A[r] = cmake(0.0, 0.0);
         }
-        bad |= hp_half_inv<B>(A, j);
+        bad |= hp_half_inv<B, ROLL>(A, j);
         if (act) {
             cplx* dst = out + (size_t)(i - 1) * BBc + j;
 #pragma unroll
@@ -447,6 +494,21 @@ __global__ void hp_leaf_fast_kernel(HpSetupArgs a) {
     const cplx ih2 = cmake(1.0 / (a.c.pml.h * a.c.pml.h), 0.0);
     if (tid < B) is2c_s[tid] = hp_lane_strip_row(tid, m, B, a.c.pml).is2c;
     auto loadM = [&](int buf, const cplx* src) { for (int e = tid; e < bb; e += nthr) Ms[buf][e] = src[e]; };
+    // the propagator of the next step is fetched into registers before the products of this step and stored to shared
+    // memory after them (the loads are L2/HBM round trips)
+    constexpr int MR = (B * B + 95) / 96;                  // registers per thread: enough for CTAs of 96 threads and more
+    const bool piped = nthr * MR >= bb && a.leaf_piped;    // narrow leaves (small problems) copy directly
+    cplx mreg[MR];
+    auto fetchM = [&](int buf, const cplx* src) {
+        if (!piped) { loadM(buf, src); return; }
+#pragma unroll
+        for (int u = 0; u < MR; ++u) { const int e = tid + u * nthr; if (e < bb) mreg[u] = src[e]; }
+    };
+    auto storeM = [&](int buf) {
+        if (!piped) return;
+#pragma unroll
+        for (int u = 0; u < MR; ++u) { const int e = tid + u * nthr; if (e < bb) Ms[buf][e] = mreg[u]; }
+    };
     auto propagate = [&](cplx* x, const cplx* M, cplx dscale) {        // x <- -M (dscale * is2c * x)
         cplx t[B], y[B];
 #pragma unroll
@@ -473,11 +535,12 @@ __global__ void hp_leaf_fast_kernel(HpSetupArgs a) {
     __syncthreads();
     for (int s = 0; s < nst; ++s) {
         const int col = q - 2 - s, i = i0 + col;
-        if (s + 1 < nst) loadM((s + 1) & 1, Finv + (size_t)(i - 2) * bb);
+        if (s + 1 < nst) fetchM((s + 1) & 1, Finv + (size_t)(i - 2) * bb);
         if (live && col < r) {
             propagate(x, Ms[s & 1], cmul(ih2, a.c.s1t[2 * i + 1]));
             wrow[col] = x[B - 1];
         }
+        if (s + 1 < nst) storeM((s + 1) & 1);
         __syncthreads();
     }
     if (live) {
@@ -493,11 +556,12 @@ __global__ void hp_leaf_fast_kernel(HpSetupArgs a) {
     __syncthreads();
     for (int s = 0; s < nst; ++s) {
         const int col = 1 + s, i = i0 + col;
-        if (s + 1 < nst) loadM((s + 1) & 1, Binv + (size_t)i * bb);
+        if (s + 1 < nst) fetchM((s + 1) & 1, Binv + (size_t)i * bb);
         if (live && col > r) {
             propagate(x, Ms[s & 1], cmul(ih2, a.c.s1t[2 * i - 1]));
             wrow[col] = x[B - 1];
         }
+        if (s + 1 < nst) storeM((s + 1) & 1);
         __syncthreads();
     }
     if (live) {
@@ -551,6 +615,172 @@ __global__ void __launch_bounds__(32) hp_sep_chain_kernel(HpSetupArgs a) {
     if (dir == 0) bad = hp_sep_chain<BB>(a.FX + o, a.FXi + o, a.PF + o, a.Sd + o, a.So + o, ns, +1, a.c.b);
     else bad = hp_sep_chain<BB>(a.BX + o, a.BXi + o, a.PB + o, a.Sd + o, a.So + o, ns, -1, a.c.b);
     if (bad) atomicOr(a.status, 2);
+}
+
+// Separator chains on half-warps (compile-time b): half-warp -> (strip, direction), lane j keeps column j of the
+// running block in registers (hp_half_inv); the operands that every lane needs (the off-diagonal block S_{j,jp},
+// T1, Xinv) are broadcast from a per-half shared-memory tile.  Same recurrence and accumulation order as
+// hp_sep_chain (csrc/hp_setup_core.h), which ran one thread per chain: 52 ms of latency at 4096^2.
+template <int B>
+__global__ void __launch_bounds__(128) hp_sep_chain_half_kernel(HpSetupArgs a) {
+    constexpr int BBc = B * B;
+    __shared__ cplx s_o[8][BBc];                 // off-diagonal block of the step (as stored in So)
+    __shared__ cplx s_t[8][BBc];                 // T1, then Xinv (row major)
+    const int lane = threadIdx.x & 31, hw = threadIdx.x >> 4;            // half-warp in the block
+    const int j = lane & 15;
+    const bool act = j < B;
+    const int chain = blockIdx.x * 8 + hw;
+    const int ns = a.lay.P - 1;
+    // idle halves of the last block follow a live chain (the shuffles and warp syncs are warp wide) without storing
+    const bool real = chain < a.nb * 2;
+    const int ch = real ? chain : a.nb * 2 - 1;
+    const int dir = (ch & 1) ? -1 : +1, lb = ch >> 1;
+    const size_t o0 = (size_t)lb * ns * BBc;
+    cplx* X = (dir > 0 ? a.FX : a.BX) + o0;
+    cplx* Xinv = (dir > 0 ? a.FXi : a.BXi) + o0;
+    cplx* Prop = (dir > 0 ? a.PF : a.PB) + o0;
+    const cplx* Sd = a.Sd + o0;
+    const cplx* So = a.So + o0;
+    cplx* so = s_o[hw];
+    cplx* st = s_t[hw];
+    const int jc = act ? j : 0;
+    cplx F[B], Xi[B];
+#pragma unroll
+    for (int r = 0; r < B; ++r) Xi[r] = cmake(0.0, 0.0);
+    int bad = 0;
+    for (int step = 0; step < ns; ++step) {
+        const int js = dir > 0 ? step : ns - 1 - step;
+#pragma unroll
+        for (int r = 0; r < B; ++r) F[r] = act ? Sd[(size_t)js * BBc + r * B + j] : cmake(0.0, 0.0);
+        if (step > 0) {
+            // A = S_{js,jp}: fwd So[js-1]^T, bwd So[js];  T1 = A Xinv_jp;  F -= T1 A^T
+            const cplx* o = So + (size_t)(dir > 0 ? js - 1 : js) * BBc;
+            __syncwarp();
+            for (int e = j; e < BBc; e += 16) so[e] = o[e];
+            __syncwarp();
+            cplx T1[B];
+#pragma unroll
+            for (int r = 0; r < B; ++r) {
+                cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+                for (int t = 0; t < B; ++t) acc = cfma(dir > 0 ? so[t * B + r] : so[r * B + t], Xi[t], acc);
+                T1[r] = acc;
+            }
+            if (act) {
+#pragma unroll
+                for (int r = 0; r < B; ++r) st[r * B + j] = T1[r];
+            }
+            __syncwarp();
+            cplx Aj[B];                                  // row j of A
+#pragma unroll
+            for (int l = 0; l < B; ++l) Aj[l] = dir > 0 ? so[l * B + jc] : so[jc * B + l];
+#pragma unroll
+            for (int r = 0; r < B; ++r) {
+                cplx acc = F[r];
+#pragma unroll
+                for (int l = 0; l < B; ++l) acc = cfms(st[r * B + l], Aj[l], acc);
+                F[r] = acc;
+            }
+        }
+        if (act && real) {
+#pragma unroll
+            for (int r = 0; r < B; ++r) X[(size_t)js * BBc + r * B + j] = F[r];
+        }
+        if (!act) {
+#pragma unroll
+            for (int r = 0; r < B; ++r) F[r] = cmake(0.0, 0.0);
+        }
+        bad |= hp_half_inv<B>(F, j);
+#pragma unroll
+        for (int r = 0; r < B; ++r) Xi[r] = F[r];
+        if (act && real) {
+#pragma unroll
+            for (int r = 0; r < B; ++r) Xinv[(size_t)js * BBc + r * B + j] = F[r];
+        }
+        const int jn = js + dir;
+        if (jn >= 0 && jn < ns) {
+            // Prop_js = -Xinv_js S_{js,jn}: fwd So[js], bwd So[js-1]^T
+            const cplx* o = So + (size_t)(dir > 0 ? js : js - 1) * BBc;
+            __syncwarp();
+            if (act) {
+#pragma unroll
+                for (int r = 0; r < B; ++r) st[r * B + j] = F[r];
+            }
+            cplx A2[B];                                  // column j of S_{js,jn}
+#pragma unroll
+            for (int t = 0; t < B; ++t) A2[t] = dir > 0 ? o[t * B + jc] : o[jc * B + t];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < B; ++r) {
+                cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+                for (int t = 0; t < B; ++t) acc = cfms(st[r * B + t], A2[t], acc);
+                if (act && real) Prop[(size_t)js * BBc + r * B + j] = acc;
+            }
+        }
+    }
+    if (bad && real && j == 0) atomicOr(a.status, 2);
+}
+
+// Corner blocks tp = G_l[(last,.),(first,kap)] (hp_leaf_corner_tp), warp -> (strip, inner leaf), lane kap < B walks
+// the leaf with the backward propagators, which all 32 lanes stage in shared memory one block row ahead.
+template <int B>
+__global__ void __launch_bounds__(128) hp_corner_warp_kernel(HpSetupArgs a) {
+    constexpr int BBc = B * B;
+    __shared__ cplx s_m[4][2][BBc];
+    __shared__ cplx s_is2c[4][B];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int P = a.lay.P, n = a.c.n;
+    const int w = blockIdx.x * 4 + wib;
+    if (w >= a.nb * (P - 2)) return;
+    const int l = 1 + w % (P - 2), lb = w / (P - 2);
+    const int m = a.m0 + lb, i0 = a.leaf_start[l] + 1, q = a.leaf_q[l];
+    const cplx* Binv = a.Binv + (size_t)lb * n * BBc;
+    const cplx ih2 = cmake(1.0 / (a.c.pml.h * a.c.pml.h), 0.0);
+    const bool act = lane < B;
+    const int kap = act ? lane : 0;
+    if (act) s_is2c[wib][lane] = hp_lane_strip_row(lane, m, B, a.c.pml).is2c;
+    constexpr int MR = (BBc + 31) / 32;
+    cplx mreg[MR];
+    auto fetch = [&](const cplx* src) {
+#pragma unroll
+        for (int u = 0; u < MR; ++u) { const int e = lane + 32 * u; if (e < BBc) mreg[u] = src[e]; }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < MR; ++u) { const int e = lane + 32 * u; if (e < BBc) s_m[wib][buf][e] = mreg[u]; }
+    };
+    cplx x[B];
+    const cplx* B0 = Binv + (size_t)(i0 - 1) * BBc;
+#pragma unroll
+    for (int r = 0; r < B; ++r) x[r] = B0[r * B + kap];
+    if (q > 1) { fetch(Binv + (size_t)i0 * BBc); stash(1); }
+    __syncwarp();
+    for (int col = 1; col < q; ++col) {
+        const int i = i0 + col;
+        if (col + 1 < q) fetch(Binv + (size_t)i * BBc);
+        const cplx* M = s_m[wib][col & 1];
+        const cplx dscale = cmul(ih2, a.c.s1t[2 * i - 1]);
+        cplx t[B], y[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) t[k] = cmul(cmul(dscale, s_is2c[wib][k]), x[k]);
+#pragma unroll
+        for (int r = 0; r < B; ++r) {
+            cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < B; ++k) acc = cfms(M[r * B + k], t[k], acc);
+            y[r] = acc;
+        }
+#pragma unroll
+        for (int r = 0; r < B; ++r) x[r] = y[r];
+        if (col + 1 < q) stash((col + 1) & 1);
+        __syncwarp();
+    }
+    if (act) {
+        cplx* tp = a.tp + ((size_t)lb * P + l) * BBc;
+#pragma unroll
+        for (int r = 0; r < B; ++r) tp[r * B + kap] = x[r];
+    }
 }
 
 // thread -> (strip, separator)
@@ -794,6 +1024,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     HpSetupArgs a;
     a.c = hp_ctx(s); a.lay = L; a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
     a.m_lo = m_lo; a.packets = s->packets; a.status = s->status;
+    a.leaf_piped = getenv("HP_LEAF_NOPIPE") ? 0 : 1;
     cplx* scratch = nullptr;
     cplx* rowbuf = nullptr;
     HP_CUDA(cudaMalloc(&scratch, per_strip * LB));
@@ -826,7 +1057,8 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
         int t1 = a.nb * P * 2;
         hp_count_launch();
         if (chain_wpb > 0 && b == 12 && !getenv("HP_CHAIN_SMEM")) {
-            hp_chain_reg_kernel<12><<<(a.nb * P + 3) / 4, 128, 0, st>>>(a);        // one warp per leaf: both chains
+            if (getenv("HP_CHAIN_UNROLL")) hp_chain_reg_kernel<12, false><<<(a.nb * P + 3) / 4, 128, 0, st>>>(a);
+            else hp_chain_reg_kernel<12, true><<<(a.nb * P + 3) / 4, 128, 0, st>>>(a);        // one warp per leaf: both chains
         } else if (chain_wpb > 0) {
             hp_chain_warp_kernel<<<(t1 + chain_wpb - 1) / chain_wpb, 32 * chain_wpb, chain_smem, st>>>(a, chain_wpb);
         } else if (small_b) hp_chain_kernel<144><<<(t1 + 63) / 64, 64, 0, st>>>(a);
@@ -837,12 +1069,15 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
         if (ns > 0) {
             if (P > 2) {
                 int t3 = a.nb * P * b;
-                hp_count_launch(); hp_corner_kernel<<<(t3 + 127) / 128, 128, 0, st>>>(a);
+                hp_count_launch();
+                if (b == 12 && !getenv("HP_SETUP_THREAD")) hp_corner_warp_kernel<12><<<(a.nb * (P - 2) + 3) / 4, 128, 0, st>>>(a);
+                else hp_corner_kernel<<<(t3 + 127) / 128, 128, 0, st>>>(a);
             }
             int t4 = a.nb * ns;
             hp_count_launch(); hp_sep_blocks_kernel<<<(t4 + 127) / 128, 128, 0, st>>>(a);
             hp_count_launch();
-            if (small_b) hp_sep_chain_kernel<144><<<(a.nb * 2 + 31) / 32, 32, 0, st>>>(a); else hp_sep_chain_kernel<HP_BMAX * HP_BMAX><<<(a.nb * 2 + 31) / 32, 32, 0, st>>>(a);
+            if (b == 12 && !getenv("HP_SETUP_THREAD")) hp_sep_chain_half_kernel<12><<<(a.nb * 2 + 7) / 8, 128, 0, st>>>(a);
+            else if (small_b) hp_sep_chain_kernel<144><<<(a.nb * 2 + 31) / 32, 32, 0, st>>>(a); else hp_sep_chain_kernel<HP_BMAX * HP_BMAX><<<(a.nb * 2 + 31) / 32, 32, 0, st>>>(a);
             hp_count_launch();
             if (small_b) hp_sep_diaginv_kernel<144><<<(t4 + 63) / 64, 64, 0, st>>>(a); else hp_sep_diaginv_kernel<HP_BMAX * HP_BMAX><<<(t4 + 63) / 64, 64, 0, st>>>(a);
             int t7 = a.nb * ns * b;
