@@ -8,6 +8,8 @@
 #include "hp_sweep4.h"
 
 #include <algorithm>
+#include <chrono>
+#include <stdio.h>
 #include <stdlib.h>
 
 struct HpSetupArgs {
@@ -471,8 +473,9 @@ __global__ void hp_leaf_kernel(HpSetupArgs a) {
 // The same leaf columns with the b x b propagators staged in shared memory (every thread of the block multiplies by
 // the same matrix at the same step) and b a compile-time constant: 12 independent accumulation chains per thread
 // instead of one.  Same operation order per entry as hp_leaf_column / hp_propagate (csrc/hp_setup_core.h).
-template <int B>
-__global__ void hp_leaf_fast_kernel(HpSetupArgs a) {
+// NT: largest CTA the instantiation is launched with (register budget: three CTAs of 128 threads per SM)
+template <int B, int NT>
+__global__ void __launch_bounds__(NT, NT <= 128 ? 3 : 1) hp_leaf_fast_kernel(HpSetupArgs a) {
     __shared__ cplx Ms[2][B * B];
     __shared__ cplx is2c_s[B];
     const int l = blockIdx.x % a.lay.P, lb = blockIdx.x / a.lay.P;
@@ -976,7 +979,21 @@ void hp_free_strips(hp_solver* s) {
     s->m_lo = 0; s->m_hi = -1; s->bytes = 0;
 }
 
+// developer trace (HP_SETUP_TRACE=1): wall-clock milliseconds since the start of hp_setup_strips at the named points
+struct HpTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    HpTrace() : on(getenv("HP_SETUP_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what, cudaStream_t st, bool sync) {
+        if (!on) return;
+        if (sync) cudaStreamSynchronize(st);
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[hp_setup] %9.2f ms  %s\n", ms, what);
+    }
+};
+
 int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cudaStream_t st) {
+    HpTrace tr;
     const int n = s->n, b = s->b, bb = b * b;
     hp_free_strips(s);
     const int nstrips = m_hi - m_lo + 1;
@@ -1003,8 +1020,11 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     HP_CUDA(cudaMemcpyAsync(s->leaf_q, s->leaf_q_h.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
     HP_CUDA(cudaMemcpyAsync(s->sep, s->sep_h.data(), sizeof(int) * std::max(ns, 1), cudaMemcpyHostToDevice, st));
     size_t pbytes = (size_t)nstrips * L.G * L.PK * sizeof(cplx);
+    tr.mark("layout chosen", st, true);
     HP_CUDA(cudaMalloc(&s->packets, pbytes));
+    tr.mark("packets allocated", st, false);
     HP_CUDA(cudaMemsetAsync(s->packets, 0, pbytes, st));
+    tr.mark("packets cleared", st, true);
     size_t xch_classic = (size_t)n + (size_t)L.G * 2 * b + (size_t)L.P * 2 * b + L.NSP + L.P;
     size_t xch_cluster = (size_t)L.G * b + (size_t)std::max(L.NS, 1) * (L.P | 1);
     HP_CUDA(cudaMalloc(&s->xch, sizeof(cplx) * 4 * std::max(xch_classic, xch_cluster)));
@@ -1019,7 +1039,9 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
                         (L.colN ? (size_t)L.NS * L.NSP : 0)) * sizeof(cplx);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    size_t cap = std::min<size_t>((size_t)(0.5 * (double)free_b), (size_t)64 << 30);   // many strips per batch: one thread per chain needs the parallelism
+    size_t cap_gb = 64;                                    // developer switch HP_SCRATCH_GB: scratch budget
+    if (const char* e = getenv("HP_SCRATCH_GB")) cap_gb = (size_t)std::max(1, atoi(e));
+    size_t cap = std::min<size_t>((size_t)(0.5 * (double)free_b), cap_gb << 30);
     int LB = (int)std::max<size_t>(1, std::min<size_t>((size_t)nstrips, cap / per_strip));
     HpSetupArgs a;
     a.c = hp_ctx(s); a.lay = L; a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
@@ -1028,6 +1050,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     cplx* scratch = nullptr;
     cplx* rowbuf = nullptr;
     HP_CUDA(cudaMalloc(&scratch, per_strip * LB));
+    tr.mark("scratch allocated", st, false);
     {
         cplx* p = scratch;
         a.Finv = p; p += (size_t)LB * n * bb;
@@ -1064,7 +1087,8 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
         } else if (small_b) hp_chain_kernel<144><<<(t1 + 63) / 64, 64, 0, st>>>(a);
         else hp_chain_kernel<HP_BMAX * HP_BMAX><<<(t1 + 63) / 64, 64, 0, st>>>(a);
         hp_count_launch();
-        if (b == 12 && !getenv("HP_CHAIN_THREAD")) hp_leaf_fast_kernel<12><<<a.nb * P, leaf_threads, 0, st>>>(a);
+        if (b == 12 && leaf_threads <= 128 && !getenv("HP_CHAIN_THREAD")) hp_leaf_fast_kernel<12, 128><<<a.nb * P, leaf_threads, 0, st>>>(a);
+        else if (b == 12 && leaf_threads <= 256 && !getenv("HP_CHAIN_THREAD")) hp_leaf_fast_kernel<12, 256><<<a.nb * P, leaf_threads, 0, st>>>(a);
         else hp_leaf_kernel<<<a.nb * P, leaf_threads, 0, st>>>(a);
         if (ns > 0) {
             if (P > 2) {
@@ -1085,6 +1109,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
         }
         HP_CUDA(cudaGetLastError());
     }
+    tr.mark("strip kernels done", st, true);
     {   // transfer matrices of the pipelined sweeps
         size_t mbytes = (size_t)nstrips * 2 * P * 4 * bb * sizeof(cplx);
         HP_CUDA(cudaMalloc(&s->mleaf, mbytes));
@@ -1114,11 +1139,13 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     }
     cudaEventRecord(e1, st);
     HP_CUDA(cudaStreamSynchronize(st));
+    tr.mark("transfer matrices / recurrence rows done", st, false);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     s->setup_ms = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     HP_CUDA(cudaFree(scratch));
+    tr.mark("scratch freed", st, false);
     int status = 0;
     HP_CUDA(cudaMemcpy(&status, s->status, sizeof(int), cudaMemcpyDeviceToHost));
     if (status) {
