@@ -311,7 +311,7 @@ __device__ __forceinline__ int hp_half_inv(cplx (&A)[B], int j) {
 }
 
 template <int B, bool ROLL>
-__global__ void __launch_bounds__(128) hp_chain_reg_kernel(HpSetupArgs a) {
+__global__ void __launch_bounds__(128, 4) hp_chain_reg_kernel(HpSetupArgs a) {
     constexpr int BBc = B * B, RH = (B + 1) / 2;
     __shared__ cplx s_tab[4][B];                 // 1/s2 at the strip rows (both halves work on the same strip)
     __shared__ cplx s_mat[4][3][BBc];            // ascending pass: Binv_i, T2, G (row major)
@@ -566,6 +566,110 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 3 : 1) hp_leaf_fast_kernel(HpS
         }
         if (s + 1 < nst) storeM((s + 1) & 1);
         __syncthreads();
+    }
+    if (live) {
+        const int it = i0 + q - 1;
+        cplx sc = cmul(ih2, a.c.s1t[2 * it + 1]);
+#pragma unroll
+        for (int kk = 0; kk < B; ++kk)
+            gl[(size_t)kk * gstride] = has_right ? cmul(cmul(sc, is2c_s[kk]), x[kk]) : cmake(0.0, 0.0);
+    }
+}
+
+// Leaf generators, warp-paced: same work split as hp_leaf_fast_kernel (CTA -> (strip, leaf), thread -> leaf column r) but
+// every warp stages the propagators it needs itself (cp.async into a per-warp double buffer) and walks only the
+// block rows between its own columns and the leaf ends, with warp syncs only.  The CTA-wide version walks the whole
+// leaf in lock step: half of the warps idle at the barrier of every step (ncu: 2.4 barrier stalls per issue).
+template <int B>
+__global__ void __launch_bounds__(128, 3) hp_leaf_warp_kernel(HpSetupArgs a) {
+    constexpr int BBc = B * B;
+    __shared__ __align__(16) cplx Ms[4][2][BBc];
+    __shared__ cplx is2c_s[B];
+    const int l = blockIdx.x % a.lay.P, lb = blockIdx.x / a.lay.P;
+    const int r = threadIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int m = a.m0 + lb, n = a.c.n;
+    const int q = a.leaf_q[l], K = a.lay.K, i0 = a.leaf_start[l] + 1;
+    const bool live = r < q, has_left = l > 0, has_right = l < a.lay.P - 1;
+    if (tid < B) is2c_s[tid] = hp_lane_strip_row(tid, m, B, a.c.pml).is2c;
+    __syncthreads();
+    const int rmin = 32 * w, rmax = min(rmin + 31, q - 1);
+    if (rmin >= q) return;                                  // warp without columns
+    const int rr = live ? r : q - 1;
+    const int k = ((rr + 1) * K - 1) / q;                  // part that owns column rr
+    const int lc0 = (q * k) / K;
+    cplx* pk = hp_packet(a, lb, l * K + k);
+    cplx* wrow = pk + (size_t)(rr - lc0) * a.lay.QP;
+    cplx* gf = pk + a.lay.offG + (rr - lc0);
+    cplx* gl = gf + (size_t)B * a.lay.CW;
+    const size_t gstride = a.lay.CW;
+    const cplx* Finv = a.Finv + (size_t)lb * n * BBc;
+    const cplx* Binv = a.Binv + (size_t)lb * n * BBc;
+    const cplx* gcol = a.gcol + (size_t)lb * n * B;
+    const cplx ih2 = cmake(1.0 / (a.c.pml.h * a.c.pml.h), 0.0);
+    auto fetch = [&](int buf, const cplx* src) {           // asynchronous copy of one b x b block, 16 bytes per lane and round
+        for (int e = lane; e < BBc; e += 32) {
+            unsigned int dst = (unsigned int)__cvta_generic_to_shared(&Ms[w][buf][e]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + e) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto landed = [&]() { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); };
+    auto propagate = [&](cplx* x, const cplx* M, cplx dscale) {        // x <- -M (dscale * is2c * x)
+        cplx t[B], y[B];
+#pragma unroll
+        for (int kk = 0; kk < B; ++kk) t[kk] = cmul(cmul(dscale, is2c_s[kk]), x[kk]);
+#pragma unroll
+        for (int aa = 0; aa < B; ++aa) {
+            cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+            for (int kk = 0; kk < B; ++kk) acc = cfms(M[aa * B + kk], t[kk], acc);
+            y[aa] = acc;
+        }
+#pragma unroll
+        for (int aa = 0; aa < B; ++aa) x[aa] = y[aa];
+    };
+    cplx x0[B], x[B];
+#pragma unroll
+    for (int kk = 0; kk < B; ++kk) x0[kk] = live ? gcol[(size_t)(i0 - 1 + r) * B + kk] : cmake(0.0, 0.0);
+    if (live) wrow[r] = x0[B - 1];
+    // leftwards: columns rmax-1 .. 0, propagator Finv of block row i = i0 + col
+#pragma unroll
+    for (int kk = 0; kk < B; ++kk) x[kk] = x0[kk];
+    {
+        const int nst = rmax;
+        if (nst > 0) fetch(0, Finv + (size_t)(i0 + rmax - 2) * BBc);
+        for (int s = 0; s < nst; ++s) {
+            const int col = rmax - 1 - s, i = i0 + col;
+            landed();                                           // block of this step is in Ms[s & 1], the other buffer is free
+            if (s + 1 < nst) fetch((s + 1) & 1, Finv + (size_t)(i - 2) * BBc);
+            if (live && col < r) {
+                propagate(x, Ms[w][s & 1], cmul(ih2, a.c.s1t[2 * i + 1]));
+                wrow[col] = x[B - 1];
+            }
+        }
+    }
+    if (live) {
+        cplx sc = cmul(ih2, a.c.s1t[2 * i0 - 1]);
+#pragma unroll
+        for (int kk = 0; kk < B; ++kk)
+            gf[(size_t)kk * gstride] = has_left ? cmul(cmul(sc, is2c_s[kk]), x[kk]) : cmake(0.0, 0.0);
+    }
+    // rightwards: columns rmin+1 .. q-1, propagator Binv of block row i = i0 + col
+#pragma unroll
+    for (int kk = 0; kk < B; ++kk) x[kk] = x0[kk];
+    {
+        const int nst = q - 1 - rmin;
+        __syncwarp();
+        if (nst > 0) fetch(0, Binv + (size_t)(i0 + rmin) * BBc);
+        for (int s = 0; s < nst; ++s) {
+            const int col = rmin + 1 + s, i = i0 + col;
+            landed();
+            if (s + 1 < nst) fetch((s + 1) & 1, Binv + (size_t)i * BBc);
+            if (live && col > r) {
+                propagate(x, Ms[w][s & 1], cmul(ih2, a.c.s1t[2 * i - 1]));
+                wrow[col] = x[B - 1];
+            }
+        }
     }
     if (live) {
         const int it = i0 + q - 1;
@@ -1039,7 +1143,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
                         (L.colN ? (size_t)L.NS * L.NSP : 0)) * sizeof(cplx);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    size_t cap_gb = 64;                                    // developer switch HP_SCRATCH_GB: scratch budget
+    size_t cap_gb = 16;                                    // scratch budget (measured: 8 and 64 GB give the same setup time); HP_SCRATCH_GB overrides
     if (const char* e = getenv("HP_SCRATCH_GB")) cap_gb = (size_t)std::max(1, atoi(e));
     size_t cap = std::min<size_t>((size_t)(0.5 * (double)free_b), cap_gb << 30);
     int LB = (int)std::max<size_t>(1, std::min<size_t>((size_t)nstrips, cap / per_strip));
@@ -1087,7 +1191,8 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
         } else if (small_b) hp_chain_kernel<144><<<(t1 + 63) / 64, 64, 0, st>>>(a);
         else hp_chain_kernel<HP_BMAX * HP_BMAX><<<(t1 + 63) / 64, 64, 0, st>>>(a);
         hp_count_launch();
-        if (b == 12 && leaf_threads <= 128 && !getenv("HP_CHAIN_THREAD")) hp_leaf_fast_kernel<12, 128><<<a.nb * P, leaf_threads, 0, st>>>(a);
+        if (b == 12 && leaf_threads <= 128 && !getenv("HP_CHAIN_THREAD") && !getenv("HP_LEAF_CTA")) hp_leaf_warp_kernel<12><<<a.nb * P, leaf_threads, 0, st>>>(a);
+        else if (b == 12 && leaf_threads <= 128 && !getenv("HP_CHAIN_THREAD")) hp_leaf_fast_kernel<12, 128><<<a.nb * P, leaf_threads, 0, st>>>(a);
         else if (b == 12 && leaf_threads <= 256 && !getenv("HP_CHAIN_THREAD")) hp_leaf_fast_kernel<12, 256><<<a.nb * P, leaf_threads, 0, st>>>(a);
         else hp_leaf_kernel<<<a.nb * P, leaf_threads, 0, st>>>(a);
         if (ns > 0) {

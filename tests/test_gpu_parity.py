@@ -233,3 +233,53 @@ def test_short_sweeps_cluster_vs_classic(hp, nstrips):
         assert s.sweep_status() == 0
         s.close()
     assert relerr(res["cluster"], res["classic"].cpu().numpy()) < 1e-12
+
+
+SETUP_SWITCHES = {
+    "shared-memory chains": ["HP_CHAIN_SMEM"],
+    "unrolled pivot loop": ["HP_CHAIN_UNROLL"],
+    "thread-per-chain separators / corners": ["HP_SETUP_THREAD"],
+    "CTA-paced leaf kernel": ["HP_LEAF_CTA"],
+    "CTA-paced leaf kernel, direct copies": ["HP_LEAF_CTA", "HP_LEAF_NOPIPE"],
+    "first generation (one thread per chain)": ["HP_CHAIN_THREAD", "HP_SETUP_THREAD"],
+}
+
+
+@pytest.mark.parametrize("n", [300, 1000])
+def test_setup_kernel_generations_agree(hp, n):
+    """The b = 12 setup kernels (register-resident Schur chains, half-warp separator chains, warp-per-leaf corners,
+    warp-paced leaf generators) against the earlier generations of the same recurrences, selected by the developer
+    switches of csrc/hp_setup.cu, and against SuperLU (the oracle) on one strip."""
+    import os
+    b = 12
+    omega = 2 * np.pi * (n / 10) + 2j
+    h = 1 / (n + 1)
+    c_mat, f_mat = orc.init_c1_f1(omega, n)
+    f = dev(f_mat.flatten().astype(np.complex128))
+    every = [k for sw in SETUP_SWITCHES.values() for k in sw]
+
+    def run(switches):
+        for k in every:
+            os.environ.pop(k, None)
+        for k in switches:
+            os.environ[k] = "1"
+        try:
+            s = hp.HelmholtzSolver(n, b, omega, 60.0, c_mat).setup_preconditioner()
+            y = s.precond_apply(f).clone()
+            rng = np.random.default_rng(5)
+            v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+            t = s.strip_apply(n // 2, dev(v)).clone()
+            assert s.sweep_status() == 0
+            s.close()
+        finally:
+            for k in every:
+                os.environ.pop(k, None)
+        return y, t, v
+
+    y0, t0, v = run([])
+    Pc = orc.SweepingPreconditioner(b, 60.0, b * h, omega, h, n, c_mat)
+    assert relerr(t0, Pc.T(n // 2, v)) < 1e-12
+    for name, sw in SETUP_SWITCHES.items():
+        y, t, _ = run(sw)
+        assert relerr(y, y0.cpu().numpy()) < 1e-11, name
+        assert relerr(t, t0.cpu().numpy()) < 1e-12, name
