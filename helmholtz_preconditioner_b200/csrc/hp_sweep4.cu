@@ -32,7 +32,8 @@
 #define HP4_CRIT 96          // critical group: warps 0-2
 #define HP4_PROD 32          // warp 3: issues every TMA copy (its lane 0), driven by the empty barriers of the rings
 #define HP4_OFF 256          // off-path group: warps 4-11
-#define HP4_THREADS (HP4_CRIT + HP4_PROD + HP4_OFF)
+#define HP4_POLL 32          // warp 12: fetches the gf partials of the right neighbour from L2 ahead of the critical group
+#define HP4_THREADS (HP4_CRIT + HP4_PROD + HP4_OFF + HP4_POLL)
 #define HP4_CW (HP4_CRIT / 32)
 
 __device__ __forceinline__ void bar_crit4() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
@@ -76,6 +77,15 @@ __device__ __noinline__ void mbar_wait4_slow(unsigned long long* bar, unsigned i
 __device__ __forceinline__ void mbar_wait4(unsigned long long* bar, unsigned int parity, unsigned int* abort_flag,
                                            volatile unsigned int* dead) {
     if (!mbar_try_cluster(bar, parity)) mbar_wait4_slow(bar, parity, abort_flag, dead);
+}
+// hand-over of plain shared-memory stores between warps of the CTA: release on the arrive, acquire on the wait
+__device__ __forceinline__ void mbar_arrive_rel4(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acq4(unsigned long long* bar, unsigned int parity, unsigned int* abort_flag,
+                                               volatile unsigned int* dead) {
+    mbar_wait4(bar, parity, abort_flag, dead);      // try_wait has acquire semantics by default
+    __syncwarp();
 }
 __device__ __forceinline__ void mbar_arrive_local(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -123,7 +133,8 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
     cplx* x3 = y0s + CW;                                         // [2][3b]     x around the leaf            (DSMEM target)
     cplx* glp = x3 + 2 * (size_t)b3;                             // [2][K][b]   partial gl of the K parts    (DSMEM target)
     cplx* rho_s = glp + 2 * (size_t)K * b;                       // [b]         rho of separator l
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(rho_s + b);
+    cplx* gfp = rho_s + b;                                       // [2][K][b]   gf partials of leaf l+1 (poll warp -> critical group)
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(gfp + 2 * (size_t)K * b);
     unsigned long long* barW = mbar;                 // [S]
     unsigned long long* barG = barW + S;             // [3]
     unsigned long long* barN = barG + 3;             // [2]
@@ -135,7 +146,9 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
     unsigned long long* eG = eW + S;                 // [3]
     unsigned long long* eN = eG + 3;                 // [2]
     unsigned long long* eR = eN + 2;                 // [2]
-    volatile unsigned int* dead = reinterpret_cast<volatile unsigned int*>(eR + 2);
+    unsigned long long* barGF = eR + 2;              // [2]  gfp filled (poll warp)
+    unsigned long long* eGF = barGF + 2;             // [2]  gfp read (critical warps)
+    volatile unsigned int* dead = reinterpret_cast<volatile unsigned int*>(eGF + 2);
 
     const cplx* pk_base = a.packets + (size_t)g * a.lay.PK;
     const size_t strip_stride = (size_t)a.lay.G * a.lay.PK;
@@ -147,6 +160,7 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
         for (int i = 0; i < S + 13; ++i) mbar_init(&mbar[i], 1);
         for (int i = 0; i < S + 3; ++i) mbar_init(&eW[i], HP4_OFF / 32);
         for (int i = 0; i < 4; ++i) mbar_init(&eN[i], HP4_CW);
+        for (int i = 0; i < 2; ++i) { mbar_init(&barGF[i], 1); mbar_init(&eGF[i], HP4_CW); }
         *dead = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
@@ -221,31 +235,15 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
             for (int ps = 0; ps < NPASS; ++ps) pre[ps] = cmake(0.0, 0.0);
             if (has_sep) {
                 mbar_wait4(&barGL[par], ph, abort_flag, dead);
-                {
-                    unsigned long long glo[NPASS], ghi[NPASS];
-                    unsigned int spins = 0;
-                    for (;;) {                                 // the warp leaves the loop as a whole
-                        bool ok = true;
+                mbar_wait_acq4(&barGF[par], ph, abort_flag, dead);
 #pragma unroll
-                        for (int ps = 0; ps < NPASS; ++ps) {
-                            const int e = e_lo + EPP * ps;
-                            glo[ps] = ghi[ps] = 0ull;
-                            if (e < b && part < K) xload(slot + a.oGP + ((size_t)(l + 1) * K + part) * b + e, glo[ps], ghi[ps]);
-                        }
-#pragma unroll
-                        for (int ps = 0; ps < NPASS; ++ps) ok = ok && xvalid(glo[ps], ghi[ps]);
-                        if (__all_sync(0xffffffffu, ok || *dead)) break;
-                        if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; }
-                        if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) *dead = 1u;
-                    }
-#pragma unroll
-                    for (int ps = 0; ps < NPASS; ++ps) {
-                        const int e = e_lo + EPP * ps;
-                        if (e < b && part < K)
-                            pre[ps] = cadd(glp[((size_t)par * K + part) * b + e],
-                                           cmake(__longlong_as_double((long long)glo[ps]), __longlong_as_double((long long)ghi[ps])));
-                    }
+                for (int ps = 0; ps < NPASS; ++ps) {
+                    const int e = e_lo + EPP * ps;
+                    if (e < b && part < K)
+                        pre[ps] = cadd(glp[((size_t)par * K + part) * b + e], gfp[((size_t)par * K + part) * b + e]);
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_rel4(&eGF[par]);        // the poll warp may refill gfp[par] (strip it+2)
                 mbar_wait4(&barR[par], ph, abort_flag, dead);
             }
             HP_TICK(0);
@@ -418,6 +416,48 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                     ring_fill4(ringW + (size_t)sl * pl.w_st, pk_base + so * strip_stride + (size_t)r0 * QP,
                                (unsigned int)((size_t)min(RC, CW - r0) * QP * sizeof(cplx)), &barW[sl]);
                 }
+            }
+        }
+    } else if (tid >= HP4_CRIT + HP4_PROD + HP4_OFF) {
+        // =====================================================================================================
+        // poll warp: the gf partials of leaf l+1 for strip it (K*b self-validating words in L2, written by the off-path
+        // groups of cluster l+1) are fetched as soon as they exist and handed to the critical group in shared memory.
+        // On the critical warps this round trip sat between the end of strip it-1 and rho(it): the CTA that finishes a
+        // strip last - the one every other CTA waits for - paid it in full.  Strips are polled in order: having seen
+        // the words of strip it-1, the re-arming of the slot of strip it (one iteration earlier, same threads) is visible.
+        // =====================================================================================================
+        if (has_sep) {
+            const int nw = K * b;
+            for (int it = 0; it < nsteps; ++it) {
+                const int par = it & 1;
+                const cplx* src = a.xch + (size_t)(it & (HP_RING - 1)) * a.slot_stride + a.oGP + (size_t)(l + 1) * K * b;
+                if (it >= 2) mbar_wait4(&eGF[par], ((it >> 1) - 1) & 1, abort_flag, dead);
+                for (int w0 = 0; w0 < nw; w0 += 32 * HP4_PW) {
+                    unsigned long long lo[HP4_PW], hi[HP4_PW];
+                    unsigned int spins = 0;
+                    for (;;) {                                 // the warp leaves the loop as a whole
+                        bool ok = true;
+#pragma unroll
+                        for (int u = 0; u < HP4_PW; ++u) {
+                            const int wd = w0 + lane + 32 * u;
+                            lo[u] = hi[u] = 0ull;
+                            if (wd < nw) xload(src + wd, lo[u], hi[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < HP4_PW; ++u) ok = ok && xvalid(lo[u], hi[u]);
+                        if (__all_sync(0xffffffffu, ok || *dead)) break;
+                        if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; }
+                        if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) *dead = 1u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < HP4_PW; ++u) {
+                        const int wd = w0 + lane + 32 * u;
+                        if (wd < nw)
+                            gfp[(size_t)par * nw + wd] = cmake(__longlong_as_double((long long)lo[u]), __longlong_as_double((long long)hi[u]));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_rel4(&barGF[par]);
             }
         }
     } else {
@@ -641,8 +681,8 @@ int hp_sweep4_plan(const HpLayout& L, int b, size_t max_smem, Hp4Plan& pl) {
     pl.g_st = al128((size_t)2 * b * L.CW * sizeof(cplx));
     pl.n_st = al128(std::max<size_t>(1, (size_t)b * L.NRQ) * sizeof(cplx));
     pl.r_st = al128((size_t)b * 3 * b * sizeof(cplx));
-    size_t small = sizeof(cplx) * ((size_t)L.CW + 2 * (size_t)L.QP + L.CW + 2 * (size_t)3 * b + 2 * (size_t)L.K * b + (size_t)b) +
-                   8 * (2 * 8 + 13 + 7) + 16;
+    size_t small = sizeof(cplx) * ((size_t)L.CW + 2 * (size_t)L.QP + L.CW + 2 * (size_t)3 * b + 4 * (size_t)L.K * b + (size_t)b) +
+                   8 * (2 * 8 + 13 + 7 + 4) + 16;
     size_t fixed = 3 * pl.g_st + 2 * pl.n_st + 2 * pl.r_st + al128(small);
     if (fixed + 1024 >= max_smem) return 1;
     size_t avail = max_smem - 1024 - fixed;

@@ -3,6 +3,7 @@
 #include "hp_internal.cuh"
 
 #define HP4_PL 3          // separators per lane in the gather of x: P-1 <= 32*HP4_PL
+#define HP4_PW 2          // words per lane and round of the poll warp (K*b <= 64 in one round)
 #define HP4_EW 3          // gathered entries per warp and batch (one batch when ceil(3b/K) <= 4*HP4_EW)
 
 struct Hp4Plan {
