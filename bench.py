@@ -207,6 +207,16 @@ def run_b200(args):
     omega, c_mat, f_mat = make_fields(w)
     n, b = w["n"], w["b"]
     N = n * n
+    # process start-up (CUDA context, loading the kernels of the library) is not part of the setup of a problem: a 96^2
+    # solve brings both up before the clock starts
+    om0 = 2 * np.pi * 9.6 + 2j
+    c0, f0 = hp.init_layered_f1(om0, 96)
+    s0 = hp.HelmholtzSolver(96, b, om0, w["const"], c0)
+    s0.setup_preconditioner()
+    s0.precond_apply(torch.from_numpy(f0.ravel().astype(np.complex128)).cuda())
+    torch.cuda.synchronize()
+    s0.close()
+    del s0
     t0 = time.time()
     s = hp.HelmholtzSolver(n, b, omega, w["const"], c_mat)
     s.setup_preconditioner()
@@ -310,6 +320,7 @@ def run_b200(args):
                         "frac_of_hbm_peak": asm_bytes / t_asm / 1e9 / peak, "nnz": nnz},
            "clocks": clk,
            "setup": {"seconds_wall": t_setup, "strip_factor_ms_device": s.setup_ms, "factor_bytes": s.precond_bytes,
+                     "note": "wall time of HelmholtzSolver(...) + setup_preconditioner() in a process whose CUDA context and kernels are already loaded",
                      "partition": {k: int(L[k]) for k in ("P", "K", "G", "QP", "CW", "NS", "NR", "PK", "colN", "NRQ", "NXG")}},
            "residual_last": hist[-1] if hist else None}
     if not args.no_tts:
