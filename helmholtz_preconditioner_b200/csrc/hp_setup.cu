@@ -1126,6 +1126,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     size_t pbytes = (size_t)nstrips * L.G * L.PK * sizeof(cplx);
     tr.mark("layout chosen", st, true);
     HP_CUDA(cudaMalloc(&s->packets, pbytes));
+    if (L.colN && ns > 0) HP_CUDA(cudaMalloc(&s->rsep, (size_t)nstrips * 2 * ns * b * 3 * b * sizeof(cplx)));
     tr.mark("packets allocated", st, false);
     HP_CUDA(cudaMemsetAsync(s->packets, 0, pbytes, st));
     tr.mark("packets cleared", st, true);
@@ -1143,7 +1144,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
                         (L.colN ? (size_t)L.NS * L.NSP : 0)) * sizeof(cplx);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    size_t cap_gb = 16;                                    // scratch budget (measured: 8 and 64 GB give the same setup time); HP_SCRATCH_GB overrides
+    size_t cap_gb = 8;                                     // scratch budget (measured: 8 and 64 GB give the same kernel time, and freeing a large scratch costs wall time); HP_SCRATCH_GB overrides
     if (const char* e = getenv("HP_SCRATCH_GB")) cap_gb = (size_t)std::max(1, atoi(e));
     size_t cap = std::min<size_t>((size_t)(0.5 * (double)free_b), cap_gb << 30);
     int LB = (int)std::max<size_t>(1, std::min<size_t>((size_t)nstrips, cap / per_strip));
@@ -1217,7 +1218,12 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     tr.mark("strip kernels done", st, true);
     {   // transfer matrices of the pipelined sweeps
         size_t mbytes = (size_t)nstrips * 2 * P * 4 * bb * sizeof(cplx);
-        HP_CUDA(cudaMalloc(&s->mleaf, mbytes));
+        // cluster layout: the transfer matrices are only an intermediate of the recurrence rows and live in the scratch of
+        // the strip kernels, which are done by now on this stream (an allocation and a free of 2.5 GB at this point cost
+        // up to 0.5 s of wall time when the allocator had to return memory first)
+        const bool m_in_scratch = L.colN && mbytes <= per_strip * (size_t)LB;
+        if (m_in_scratch) s->mleaf = scratch;
+        else HP_CUDA(cudaMalloc(&s->mleaf, mbytes));
         HP_CUDA(cudaMemsetAsync(s->mleaf, 0, mbytes, st));
         size_t smem = sizeof(cplx) * 2 * 2 * b * L.QP;
         HP_CUDA(cudaFuncSetAttribute(hp_mleaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1228,7 +1234,6 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
             // cluster kernel: the separator recurrence rows replace the per-leaf transfer matrices
             if (ns > 0) {
                 size_t rbytes = (size_t)nstrips * 2 * ns * b * 3 * b * sizeof(cplx);
-                HP_CUDA(cudaMalloc(&s->rsep, rbytes));
                 HP_CUDA(cudaMemsetAsync(s->rsep, 0, rbytes, st));
                 hp_count_launch(); hp_rsep_kernel<<<nstrips * 2 * ns, 128, 0, st>>>(s->mleaf, L, s->sep, m_lo, m_hi, b,
                                                                                  1.0 / (s->pml.h * s->pml.h), s->s2t, s->is1t, s->rsep);
@@ -1236,7 +1241,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
                 s->bytes += (int64_t)rbytes;
             }
             HP_CUDA(cudaStreamSynchronize(st));
-            HP_CUDA(cudaFree(s->mleaf));
+            if (!m_in_scratch) HP_CUDA(cudaFree(s->mleaf));
             s->mleaf = nullptr;
         } else {
             s->bytes += (int64_t)mbytes;
