@@ -235,6 +235,16 @@ def test_short_sweeps_cluster_vs_classic(hp, nstrips):
     assert relerr(res["cluster"], res["classic"].cpu().numpy()) < 1e-12
 
 
+def oracle_strip_T(m, v, b, const, omega, n, c_mat):
+    """T_m v with one SuperLU factorisation (the oracle class factors every strip in its constructor)."""
+    import scipy.sparse.linalg
+    h = 1 / (n + 1)
+    lu = scipy.sparse.linalg.splu(orc.get_Hm(m, b, const, b * h, omega, h, n, c_mat).tocsc())
+    t = np.zeros(b * n, dtype=np.complex128)
+    t[-n:] = v
+    return lu.solve(t)[-n:]
+
+
 SETUP_SWITCHES = {
     "shared-memory chains": ["HP_CHAIN_SMEM"],
     "unrolled pivot loop": ["HP_CHAIN_UNROLL"],
@@ -277,9 +287,26 @@ def test_setup_kernel_generations_agree(hp, n):
         return y, t, v
 
     y0, t0, v = run([])
-    Pc = orc.SweepingPreconditioner(b, 60.0, b * h, omega, h, n, c_mat)
-    assert relerr(t0, Pc.T(n // 2, v)) < 1e-12
+    assert relerr(t0, oracle_strip_T(n // 2, v, b, 60.0, omega, n, c_mat)) < 1e-12
     for name, sw in SETUP_SWITCHES.items():
         y, t, _ = run(sw)
         assert relerr(y, y0.cpu().numpy()) < 1e-11, name
         assert relerr(t, t0.cpu().numpy()) < 1e-12, name
+
+
+@pytest.mark.parametrize("n,P,K", [(2048, 8, 4), (1600, 10, 2)])
+def test_wide_leaves_vs_oracle(hp, n, P, K):
+    """Leaves wider than 128 columns (what an 8192^2 problem gets with at most 33 clusters): the b = 12 setup takes the
+    256-thread leaf kernel there; a few strips against SuperLU, set up as a short strip range."""
+    b = 12
+    omega = 2 * np.pi * (n / 10) + 2j
+    c_mat = orc.init_c1_f1(omega, n)[0]
+    m_lo, m_hi = n // 2, n // 2 + 3
+    s = hp.HelmholtzSolver(n, b, omega, 60.0, c_mat).setup_preconditioner(P=P, K=K, m_lo=m_lo, m_hi=m_hi, layout="classic")
+    assert s.layout()["QP"] > 128
+    rng = np.random.default_rng(11)
+    for m in (m_lo, m_hi):
+        v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        assert relerr(s.strip_apply(m, dev(v)), oracle_strip_T(m, v, b, 60.0, omega, n, c_mat)) < 1e-12
+    assert s.sweep_status() == 0
+    s.close()
