@@ -220,6 +220,19 @@ __device__ __forceinline__ cplx hp_shfl16(cplx v, int src) {
     return cmake(__shfl_sync(0xffffffffu, v.x, src, 16), __shfl_sync(0xffffffffu, v.y, src, 16));
 }
 
+// 1/a as conj(a)/|a|^2: one division instead of the two of Smith's algorithm (the entries of the Schur blocks are of
+// the order 1/h^2, far from the overflow range of |a|^2)
+__device__ __forceinline__ cplx hp_crecip(cplx a) {
+    const double r = 1.0 / fma(a.x, a.x, a.y * a.y);
+    return cmake(a.x * r, -a.y * r);
+}
+#ifdef HP_PIVOT_SMITH            // developer switch: the earlier pivot rule (largest modulus, Smith's reciprocal)
+#define HP_PIVOT_NORM(a) cabs2(a)
+#define HP_PIVOT_INV(a) cinv(a)
+#else                            // |re| + |im| is within sqrt(2) of the modulus: as good a pivot rule, one add per entry
+#define HP_PIVOT_NORM(a) (fabs((a).x) + fabs((a).y))
+#define HP_PIVOT_INV(a) hp_crecip(a)
+#endif
 // in-place inverse of the B x B matrix whose column j is A[0..B) of lane j of each half-warp (partial pivoting).
 // The pivot loop is NOT unrolled (unrolled, the kernel is ~90 KB of straight-line code and stalls on instruction
 // fetch): after every step the rows are rotated by one register, so that the pivot row is always A[0] and the
@@ -272,10 +285,10 @@ __device__ __forceinline__ int hp_half_inv(cplx (&A)[B], int j) {
     for (int p = 0; p < B; ++p) {
         // logical row i >= p sits in A[i - p]; pivot search in lane p, which holds column p
         int k_own = 0;
-        double best = cabs2(A[0]);
+        double best = HP_PIVOT_NORM(A[0]);
 #pragma unroll
         for (int k = 1; k < B; ++k) {
-            const double v = cabs2(A[k]);
+            const double v = HP_PIVOT_NORM(A[k]);
             if (k < B - p && v > best) { best = v; k_own = k; }
         }
         const int kr = __shfl_sync(0xffffffffu, k_own, p, 16);
@@ -286,7 +299,7 @@ __device__ __forceinline__ int hp_half_inv(cplx (&A)[B], int j) {
             for (int k = 1; k < B; ++k)
                 if (k == kr) { const cplx t = A[k]; A[k] = A[0]; A[0] = t; }
         }
-        const cplx d = cinv(hp_shfl16(A[0], p));
+        const cplx d = HP_PIVOT_INV(hp_shfl16(A[0], p));
         const bool isp = j == p;
         const cplx prow = cmul(isp ? cmake(1.0, 0.0) : A[0], d);
         // eliminate the other rows and rotate: new A[k-1] = updated A[k], new A[B-1] = pivot row
