@@ -6,6 +6,8 @@
 // one process are expected on one stream (they share the partial buffer).
 #include "hp_internal.cuh"
 
+#include <stdlib.h>
+
 #define HP_RED_THREADS 256
 #define HP_RED_MAX_CTAS 1184   // 8 per SM on a 148-SM part
 
@@ -54,6 +56,56 @@ __global__ void __launch_bounds__(HP_RED_THREADS) hp_reduce_kernel(int64_t n, co
     if (threadIdx.x == 0) {
         cplx t = wsum[0];
         for (int w = 1; w < HP_RED_THREADS / 32; ++w) t = cadd(t, wsum[w]);
+        partials[blockIdx.x] = t;
+        __threadfence();
+        unsigned int k = atomicAdd(ticket, 1u);
+        last = (k == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 32) {
+        __threadfence();
+        cplx t = cmake(0.0, 0.0);
+        const volatile double* pv = (const volatile double*)partials;   // written by other CTAs: bypass L1
+        for (int c = threadIdx.x; c < (int)gridDim.x; c += 32) t = cadd(t, cmake(pv[2 * c], pv[2 * c + 1]));
+        t = hp_warp_sum(t);
+        if (threadIdx.x == 0) {
+            if (MODE == 1) t = cmake(sqrt(t.x), 0.0);
+            *out = t;
+            *ticket = 0u;
+        }
+    }
+}
+
+// Fused Gram-Schmidt step: w -= h v (h read from device memory) and, in the same pass, the reduction the next step needs
+// from the updated w: MODE 0 out = conj(vn) . w (the next coefficient), MODE 1 out = ||w|| (after the last vector).
+// Same grid, same slices and the same accumulation order as hp_reduce_kernel, so the results are bit-identical to the
+// separate axpy and reduction (4 passes over n-vectors instead of 5).
+template <int MODE>
+__global__ void __launch_bounds__(HP_RED_THREADS) hp_axpy_reduce_kernel(int64_t n, const cplx* __restrict__ hcoef,
+        const cplx* __restrict__ v, cplx* __restrict__ w, const cplx* __restrict__ vn, cplx* __restrict__ partials,
+        unsigned int* ticket, cplx* __restrict__ out) {
+    __shared__ cplx wsum[HP_RED_THREADS / 32];
+    __shared__ bool last;
+    const cplx a = cscale(-1.0, *hcoef);
+    cplx acc = cmake(0.0, 0.0);
+    const int64_t stride = (int64_t)gridDim.x * HP_RED_THREADS;
+    for (int64_t e = (int64_t)blockIdx.x * HP_RED_THREADS + threadIdx.x; e < n; e += stride) {
+        const cplx b = cfma(a, v[e], w[e]);
+        w[e] = b;
+        if (MODE == 0) {
+            const cplx x = vn[e];
+            acc.x = fma(x.x, b.x, fma(x.y, b.y, acc.x));
+            acc.y = fma(x.x, b.y, fma(-x.y, b.x, acc.y));
+        } else {
+            acc.x = fma(b.x, b.x, fma(b.y, b.y, acc.x));
+        }
+    }
+    acc = hp_warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cplx t = wsum[0];
+        for (int k = 1; k < HP_RED_THREADS / 32; ++k) t = cadd(t, wsum[k]);
         partials[blockIdx.x] = t;
         __threadfence();
         unsigned int k = atomicAdd(ticket, 1u);
@@ -160,15 +212,25 @@ extern "C" int hp_mgs(int64_t n, int k, const double* V, int64_t ldv, double* w,
     cudaStream_t st = (cudaStream_t)stream;
     cplx* h = (cplx*)hcol;
     const cplx* Vc = (const cplx*)V;
-    hp_count_launch(); hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, (const cplx*)w, (const cplx*)w, g_partials,
-                                                                  g_ticket, h + k + 1);       // h0
-    for (int j = 0; j < k; ++j) {
-        hp_count_launch(); hp_reduce_kernel<0><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, Vc + (size_t)j * ldv, (const cplx*)w,
-                                                                      g_partials, g_ticket, h + j);
-        hp_count_launch(); hp_axpy_dev_kernel<<<hp_ew_grid(n), 256, 0, st>>>(n, h + j, -1.0, Vc + (size_t)j * ldv, (cplx*)w);
+    cplx* wc = (cplx*)w;
+    const unsigned g = hp_red_grid(n);
+    hp_count_launch(); hp_reduce_kernel<1><<<g, HP_RED_THREADS, 0, st>>>(n, wc, wc, g_partials, g_ticket, h + k + 1);       // h0
+    if (k == 0 || getenv("HP_MGS_UNFUSED")) {
+        for (int j = 0; j < k; ++j) {
+            hp_count_launch(); hp_reduce_kernel<0><<<g, HP_RED_THREADS, 0, st>>>(n, Vc + (size_t)j * ldv, wc, g_partials, g_ticket, h + j);
+            hp_count_launch(); hp_axpy_dev_kernel<<<hp_ew_grid(n), 256, 0, st>>>(n, h + j, -1.0, Vc + (size_t)j * ldv, wc);
+        }
+        hp_count_launch(); hp_reduce_kernel<1><<<g, HP_RED_THREADS, 0, st>>>(n, wc, wc, g_partials, g_ticket, h + k);        // h1
+    } else {
+        // h_0 = v_0 . w;  then every pass subtracts h_j v_j and forms what comes next from the updated w
+        hp_count_launch(); hp_reduce_kernel<0><<<g, HP_RED_THREADS, 0, st>>>(n, Vc, wc, g_partials, g_ticket, h);
+        for (int j = 0; j + 1 < k; ++j) {
+            hp_count_launch(); hp_axpy_reduce_kernel<0><<<g, HP_RED_THREADS, 0, st>>>(n, h + j, Vc + (size_t)j * ldv, wc, Vc + (size_t)(j + 1) * ldv,
+                                                                              g_partials, g_ticket, h + j + 1);
+        }
+        hp_count_launch(); hp_axpy_reduce_kernel<1><<<g, HP_RED_THREADS, 0, st>>>(n, h + k - 1, Vc + (size_t)(k - 1) * ldv, wc, wc, g_partials, g_ticket,
+                                                                          h + k);                                     // h1
     }
-    hp_count_launch(); hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, st>>>(n, (const cplx*)w, (const cplx*)w, g_partials,
-                                                                  g_ticket, h + k);           // h1
     HP_CUDA(cudaGetLastError());
     return 0;
 }

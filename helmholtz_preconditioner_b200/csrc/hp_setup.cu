@@ -903,6 +903,74 @@ __global__ void __launch_bounds__(128) hp_corner_warp_kernel(HpSetupArgs a) {
     }
 }
 
+// The same walk with two inner leaves per warp (half-warp -> leaf, lane kap < B of the half -> source row): 24 of 32
+// lanes carry a product instead of 12.  Each half stages its own propagators (its leaf, possibly one block row shorter
+// than the other's) with 16 lanes; the loop runs to the longer leaf with warp-wide syncs.
+template <int B>
+__global__ void __launch_bounds__(128) hp_corner_half_kernel(HpSetupArgs a) {
+    constexpr int BBc = B * B;
+    __shared__ cplx s_m[8][2][BBc];
+    __shared__ cplx s_is2c[8][B];
+    const int lane = threadIdx.x & 31, hw = threadIdx.x >> 4, j = lane & 15;
+    const int P = a.lay.P, n = a.c.n;
+    const int total = a.nb * (P - 2);
+    const int t = blockIdx.x * 8 + hw;
+    const bool real = t < total;                          // the idle half of the last warp follows the last leaf, without storing
+    const int tt = real ? t : total - 1;
+    const int l = 1 + tt % (P - 2), lb = tt / (P - 2);
+    const int m = a.m0 + lb, i0 = a.leaf_start[l] + 1, q = a.leaf_q[l];
+    const cplx* Binv = a.Binv + (size_t)lb * n * BBc;
+    const cplx ih2 = cmake(1.0 / (a.c.pml.h * a.c.pml.h), 0.0);
+    const bool act = j < B;
+    const int kap = act ? j : 0;
+    if (act) s_is2c[hw][j] = hp_lane_strip_row(j, m, B, a.c.pml).is2c;
+    constexpr int MR = (BBc + 15) / 16;
+    cplx mreg[MR];
+    auto fetch = [&](const cplx* src) {
+#pragma unroll
+        for (int u = 0; u < MR; ++u) { const int e = j + 16 * u; if (e < BBc) mreg[u] = src[e]; }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < MR; ++u) { const int e = j + 16 * u; if (e < BBc) s_m[hw][buf][e] = mreg[u]; }
+    };
+    cplx x[B];
+    const cplx* B0 = Binv + (size_t)(i0 - 1) * BBc;
+#pragma unroll
+    for (int r = 0; r < B; ++r) x[r] = B0[r * B + kap];
+    if (q > 1) { fetch(Binv + (size_t)i0 * BBc); stash(1); }
+    const int qmax = max(q, __shfl_xor_sync(0xffffffffu, q, 16));
+    __syncwarp();
+    for (int col = 1; col < qmax; ++col) {
+        const int i = i0 + col;
+        const bool on = col < q;
+        if (on && col + 1 < q) fetch(Binv + (size_t)i * BBc);
+        if (on) {
+            const cplx* M = s_m[hw][col & 1];
+            const cplx dscale = cmul(ih2, a.c.s1t[2 * i - 1]);
+            cplx tv[B], y[B];
+#pragma unroll
+            for (int k = 0; k < B; ++k) tv[k] = cmul(cmul(dscale, s_is2c[hw][k]), x[k]);
+#pragma unroll
+            for (int r = 0; r < B; ++r) {
+                cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < B; ++k) acc = cfms(M[r * B + k], tv[k], acc);
+                y[r] = acc;
+            }
+#pragma unroll
+            for (int r = 0; r < B; ++r) x[r] = y[r];
+        }
+        if (on && col + 1 < q) stash((col + 1) & 1);
+        __syncwarp();
+    }
+    if (act && real) {
+        cplx* tp = a.tp + ((size_t)lb * P + l) * BBc;
+#pragma unroll
+        for (int r = 0; r < B; ++r) tp[r * B + kap] = x[r];
+    }
+}
+
 // thread -> (strip, separator)
 template <int BB>
 __global__ void __launch_bounds__(64) hp_sep_diaginv_kernel(HpSetupArgs a) {
@@ -1213,7 +1281,8 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
             if (P > 2) {
                 int t3 = a.nb * P * b;
                 hp_count_launch();
-                if (b == 12 && !getenv("HP_SETUP_THREAD")) hp_corner_warp_kernel<12><<<(a.nb * (P - 2) + 3) / 4, 128, 0, st>>>(a);
+                if (b == 12 && !getenv("HP_SETUP_THREAD") && !getenv("HP_CORNER_WARP")) hp_corner_half_kernel<12><<<(a.nb * (P - 2) + 7) / 8, 128, 0, st>>>(a);
+                else if (b == 12 && !getenv("HP_SETUP_THREAD")) hp_corner_warp_kernel<12><<<(a.nb * (P - 2) + 3) / 4, 128, 0, st>>>(a);
                 else hp_corner_kernel<<<(t3 + 127) / 128, 128, 0, st>>>(a);
             }
             int t4 = a.nb * ns;

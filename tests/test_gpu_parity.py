@@ -183,6 +183,23 @@ def test_krylov_kernels(hp):
     assert np.allclose(h, hr, rtol=1e-12) and abs(h1 - np.linalg.norm(wr)) < 1e-11 * h1
     assert abs(h0 - np.linalg.norm(w)) < 1e-12 * h0
     assert relerr(wd, wr) < 1e-13
+    # fused passes (w -= h_j v_j together with the next coefficient) against the separate dot / axpy launches: the
+    # slices and the accumulation order are the same, so the results are bit-identical
+    import os
+    for kk in (0, 1, 2, k):
+        res = []
+        for unfused in (False, True):
+            os.environ.pop("HP_MGS_UNFUSED", None)
+            if unfused:
+                os.environ["HP_MGS_UNFUSED"] = "1"
+            w2 = dev(w)
+            try:
+                hh, a1, a0 = vec.mgs(Vd, kk, w2)
+            finally:
+                os.environ.pop("HP_MGS_UNFUSED", None)
+            res.append((hh.copy(), a1, a0, w2.cpu().numpy()))
+        assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1] and res[0][2] == res[1][2]
+        assert np.array_equal(res[0][3], res[1][3])
     x = dev(w)
     y = rng.standard_normal(k) + 1j * rng.standard_normal(k)
     vec.combine(Vd, y, x)
@@ -249,6 +266,7 @@ SETUP_SWITCHES = {
     "shared-memory chains": ["HP_CHAIN_SMEM"],
     "unrolled pivot loop": ["HP_CHAIN_UNROLL"],
     "thread-per-chain separators / corners": ["HP_SETUP_THREAD"],
+    "one inner leaf per warp in the corner kernel": ["HP_CORNER_WARP"],
     "CTA-paced leaf kernel": ["HP_LEAF_CTA"],
     "CTA-paced leaf kernel, direct copies": ["HP_LEAF_CTA", "HP_LEAF_NOPIPE"],
     "first generation (one thread per chain)": ["HP_CHAIN_THREAD", "HP_SETUP_THREAD"],
