@@ -243,7 +243,7 @@ __device__ __forceinline__ int hp_half_inv(cplx (&A)[B], int j) {
     static_assert(B <= 16, "pivot indices are packed in 4 bits");
     int bad = 0;
     unsigned long long pivs = 0ull;
-    if (!ROLL) {                                     // developer variant: fully unrolled pivot loop
+    if constexpr (!ROLL) {                           // developer variant: fully unrolled pivot loop
         int piv[B];
 #pragma unroll
         for (int p = 0; p < B; ++p) {
@@ -280,7 +280,7 @@ __device__ __forceinline__ int hp_half_inv(cplx (&A)[B], int j) {
             }
         }
         return bad;
-    }
+    } else {
 #pragma unroll 1
     for (int p = 0; p < B; ++p) {
         // logical row i >= p sits in A[i - p]; pivot search in lane p, which holds column p
@@ -321,6 +321,7 @@ __device__ __forceinline__ int hp_half_inv(cplx (&A)[B], int j) {
         }
     }
     return bad;
+    }
 }
 
 template <int B, bool ROLL>
