@@ -1007,6 +1007,58 @@ __global__ void __launch_bounds__(128) hp_sep_rows_kernel(HpSetupArgs a, cplx* r
     }
 }
 
+// Cluster layout, compile-time b: the same rows of N (hp_sep_row) written straight into the packets.  Column (j, kap)
+// of N is contiguous in the packet of its CTA (Np[kap][NRQ]), so the b entries a thread forms per separator are one run of
+// b*16 bytes; the generic kernel above goes through a row buffer and a scatter loop (two more passes over N with
+// 16-byte accesses 6 KB apart).
+template <int B>
+__global__ void __launch_bounds__(128) hp_sep_rows_direct_kernel(HpSetupArgs a) {
+    constexpr int BBc = B * B;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ns = a.lay.P - 1;
+    if (t >= a.nb * ns * B) return;
+    const int kap = t % B, j = (t / B) % ns, lb = t / (B * ns);
+    const size_t o = (size_t)lb * ns * BBc;
+    const cplx* Njj = a.Njj + o + (size_t)j * BBc;
+    const cplx* PF = a.PF + o;
+    const cplx* PB = a.PB + o;
+    const int NRQ = a.lay.NRQ, K = a.lay.K;
+    cplx* pk0 = hp_packet(a, lb, j * K) + a.lay.offN + (size_t)kap * NRQ;     // part 0 of cluster j, column kap
+    const size_t pstride = a.lay.PK;                                            // next CTA of the cluster
+    auto store = [&](int i, cplx v) { const int part = i / NRQ; pk0[(size_t)part * pstride + (i - part * NRQ)] = v; };
+    cplx x0[B], x[B], y[B];
+#pragma unroll
+    for (int r = 0; r < B; ++r) { x0[r] = Njj[r * B + kap]; store(j * B + r, x0[r]); }
+#pragma unroll
+    for (int r = 0; r < B; ++r) x[r] = x0[r];
+    for (int jj = j - 1; jj >= 0; --jj) {
+        const cplx* M = PF + (size_t)jj * BBc;
+#pragma unroll
+        for (int r = 0; r < B; ++r) {
+            cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < B; ++k) acc = cfma(M[r * B + k], x[k], acc);
+            y[r] = acc;
+        }
+#pragma unroll
+        for (int r = 0; r < B; ++r) { x[r] = y[r]; store(jj * B + r, y[r]); }
+    }
+#pragma unroll
+    for (int r = 0; r < B; ++r) x[r] = x0[r];
+    for (int jj = j + 1; jj < ns; ++jj) {
+        const cplx* M = PB + (size_t)jj * BBc;
+#pragma unroll
+        for (int r = 0; r < B; ++r) {
+            cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < B; ++k) acc = cfma(M[r * B + k], x[k], acc);
+            y[r] = acc;
+        }
+#pragma unroll
+        for (int r = 0; r < B; ++r) { x[r] = y[r]; store(jj * B + r, y[r]); }
+    }
+}
+
 // Separator recurrence rows of the cluster sweep kernel (csrc/hp_sweep4.cu).  With x3 = [x_{j-1}; x_j; x_{j+1}] of the
 // previous strip of the sweep, rho_j(t) = rho_b(t) - R_j(t) x3(t-1),
 //   R_j[i][0..b)   = M_j[b+i][kap]                                   (gl of leaf j from x_{j-1})
@@ -1294,7 +1346,9 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
             hp_count_launch();
             if (small_b) hp_sep_diaginv_kernel<144><<<(t4 + 63) / 64, 64, 0, st>>>(a); else hp_sep_diaginv_kernel<HP_BMAX * HP_BMAX><<<(t4 + 63) / 64, 64, 0, st>>>(a);
             int t7 = a.nb * ns * b;
-            hp_count_launch(); hp_sep_rows_kernel<<<(t7 + 127) / 128, 128, 0, st>>>(a, rowbuf);
+            hp_count_launch();
+            if (b == 12 && L.colN && !getenv("HP_SEP_ROWS_BUF")) hp_sep_rows_direct_kernel<12><<<(t7 + 127) / 128, 128, 0, st>>>(a);
+            else hp_sep_rows_kernel<<<(t7 + 127) / 128, 128, 0, st>>>(a, rowbuf);
         }
         HP_CUDA(cudaGetLastError());
     }

@@ -267,6 +267,7 @@ SETUP_SWITCHES = {
     "unrolled pivot loop": ["HP_CHAIN_UNROLL"],
     "thread-per-chain separators / corners": ["HP_SETUP_THREAD"],
     "one inner leaf per warp in the corner kernel": ["HP_CORNER_WARP"],
+    "rows of N through the row buffer": ["HP_SEP_ROWS_BUF"],
     "CTA-paced leaf kernel": ["HP_LEAF_CTA"],
     "CTA-paced leaf kernel, direct copies": ["HP_LEAF_CTA", "HP_LEAF_NOPIPE"],
     "first generation (one thread per chain)": ["HP_CHAIN_THREAD", "HP_SETUP_THREAD"],

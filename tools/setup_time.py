@@ -9,14 +9,14 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 b = 12
 omega = 2 * np.pi * n / 10 + 2j
 c_mat, f_mat = hp.init_layered_f1(omega, n)
-SW = ["HP_CHAIN_SMEM", "HP_CHAIN_UNROLL", "HP_SETUP_THREAD", "HP_LEAF_NOPIPE", "HP_LEAF_CTA", "HP_CORNER_WARP"]
+SW = ["HP_CHAIN_SMEM", "HP_CHAIN_UNROLL", "HP_SETUP_THREAD", "HP_LEAF_NOPIPE", "HP_LEAF_CTA", "HP_CORNER_WARP", "HP_SEP_ROWS_BUF"]
 QUICK = len(sys.argv) > 2 and sys.argv[2] == "quick"
 configs = [("default", []), ("old chain", ["HP_CHAIN_SMEM"]), ("unrolled inverse", ["HP_CHAIN_UNROLL"]),
            ("thread sep/corner", ["HP_SETUP_THREAD"]), ("leaf CTA-paced", ["HP_LEAF_CTA"]),
            ("leaf CTA, not piped", ["HP_LEAF_CTA", "HP_LEAF_NOPIPE"]),
            ("all old", ["HP_CHAIN_SMEM", "HP_SETUP_THREAD", "HP_LEAF_CTA", "HP_LEAF_NOPIPE"]), ("default", [])]
 if QUICK:
-    configs = [("default", []), ("corner: leaf per warp", ["HP_CORNER_WARP"]), ("default", [])]
+    configs = [("default", []), ("corner: leaf per warp", ["HP_CORNER_WARP"]), ("N rows via buffer", ["HP_SEP_ROWS_BUF"]), ("default", [])]
 ref = None
 x = torch.from_numpy(f_mat.ravel().astype(np.complex128)).cuda()
 for name, sw in configs:
