@@ -102,3 +102,29 @@ def test_strip_apply_medium(hh):
         mod.b, mod.n, mod.m, mod.part, mod.W, mod.G, mod.N = b, n, m, pt, W, G, N
         v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
         assert rel(mod.apply(v), Pc.T(m, v)) < 1e-12
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_half_warp_inverse_model(seed):
+    """The rolled, register-rotating Gauss-Jordan of the b = 12 setup kernels (hp_half_inv, csrc/hp_setup.cu) as a lane-level
+    numpy model: blocks that need no row exchange, blocks that need one at every step, a Schur block of a strip."""
+    rng = np.random.default_rng(seed)
+    B = 12
+    if seed < 2:                                     # diagonally dominant: the pivot word is the identity permutation
+        A = rng.standard_normal((B, B)) + 1j * rng.standard_normal((B, B)) + 40 * np.eye(B)
+    elif seed < 4:                                   # dominant anti-diagonal: a row exchange at (almost) every step
+        A = rng.standard_normal((B, B)) + 1j * rng.standard_normal((B, B)) + 40 * np.fliplr(np.eye(B))
+    else:                                            # diagonal block of a strip operator (tridiagonal, complex symmetric)
+        n, b = 40, B
+        omega = 2 * np.pi * 4 + 2j
+        h = 1 / (n + 1)
+        c_mat = orc.init_c1_f1(omega, n)[0]
+        D, L, U = sm.strip_blocks(b + 5 + seed, b, 60.0, b * h, omega, h, n, c_mat)
+        A = np.asarray(D[n // 2])
+    Ai, pivs = sm.half_warp_inverse_model(A)
+    assert np.linalg.norm(Ai @ A - np.eye(B)) < 1e-12 * np.linalg.cond(A)
+    assert np.allclose(Ai, np.linalg.inv(A), rtol=1e-10, atol=1e-12 * np.abs(np.linalg.inv(A)).max())
+    if seed < 2:
+        assert pivs == sum(p << (4 * p) for p in range(B))
+    elif seed < 4:
+        assert pivs != sum(p << (4 * p) for p in range(B))

@@ -142,3 +142,39 @@ class StripModel:
         for j in range(ns):
             y[int(pt["sep"][j])] = xs[j, b - 1]
         return y
+
+
+def half_warp_inverse_model(A):
+    """Lane-level model of hp_half_inv (csrc/hp_setup.cu): lane j of a half-warp holds column j of the B x B block in
+    "registers" R[k][j]; the pivot loop is rolled, after every step the rows rotate by one register so that the pivot row
+    is always register 0; pivot rows are kept as 4-bit fields; the row exchanges are undone on the columns (lanes) at the
+    end.  Returns (inverse, pivot word)."""
+    A = np.array(A, dtype=np.complex128)
+    B = A.shape[0]
+    assert A.shape == (B, B) and B <= 16
+    R = A.copy()                                    # R[k, j]: register k of lane j
+    pivs = 0
+    for p in range(B):
+        # pivot search inside lane p over the live registers 0 .. B-1-p (|re| + |im|, first maximum)
+        col = R[:B - p, p]
+        norm = np.abs(col.real) + np.abs(col.imag)
+        kr = int(np.argmax(norm))
+        if norm[kr] == 0.0:
+            raise ZeroDivisionError("singular block")
+        pivs |= (p + kr) << (4 * p)
+        if kr != 0:
+            R[[0, kr], :] = R[[kr, 0], :]
+        a = R[0, p]
+        r = 1.0 / (a.real * a.real + a.imag * a.imag)
+        d = complex(a.real * r, -a.imag * r)        # conj(a) / |a|^2
+        prow = np.where(np.arange(B) == p, 1.0 + 0j, R[0, :]) * d
+        f = R[1:, p].copy()                         # multipliers, broadcast from lane p
+        base = R[1:, :].copy()
+        base[:, p] = 0.0
+        R[:B - 1, :] = base - np.outer(f, prow)     # eliminated rows move up by one register
+        R[B - 1, :] = prow                          # the pivot row goes to the end
+    for p in range(B - 1, -1, -1):                  # after B rotations register k holds row k again
+        r = (pivs >> (4 * p)) & 15
+        if r != p:
+            R[:, [p, r]] = R[:, [r, p]]
+    return R, pivs
