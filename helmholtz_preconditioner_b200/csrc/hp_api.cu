@@ -62,17 +62,8 @@ extern "C" int hp_device_ok(void) {
     return 1;
 }
 
-extern "C" int hp_create(hp_solver** out, int n, int b, double omega_re, double omega_im, double cst,
-                         const double* c_mat, int c_is_device, void* stream) {
-    if (!out) { hp_set_error("hp_create: null output"); return 1; }
-    *out = nullptr;
-    if (n < 2 || b < 1 || b > HP_BMAX || b > n) {
-        hp_set_error("hp_create: need 2 <= n, 1 <= b <= min(n, %d); got n=%d b=%d", HP_BMAX, n, b);
-        return 1;
-    }
-    if (!hp_device_ok()) { hp_set_error("hp_create: no CUDA device (this library has no CPU path)"); return 2; }
-    cudaStream_t st = (cudaStream_t)stream;
-    hp_solver* s = new hp_solver();
+static int hp_create_fill(hp_solver* s, int n, int b, double omega_re, double omega_im, double cst, const double* c_mat,
+                          int c_is_device, cudaStream_t st) {
     s->n = n; s->b = b;
     double h = 1.0 / (double)(n + 1);                     // code.py:443
     s->pml.cst = cst; s->pml.h = h; s->pml.eta = (double)b * h;   // code.py:444
@@ -94,6 +85,22 @@ extern "C" int hp_create(hp_solver** out, int n, int b, double omega_re, double 
     s->s2t_h.resize(2 * n + 3);
     HP_CUDA(cudaMemcpyAsync(s->s2t_h.data(), s->s2t, tl, cudaMemcpyDeviceToHost, st));
     HP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int hp_create(hp_solver** out, int n, int b, double omega_re, double omega_im, double cst,
+                         const double* c_mat, int c_is_device, void* stream) {
+    if (!out) { hp_set_error("hp_create: null output"); return 1; }
+    *out = nullptr;
+    if (n < 2 || b < 1 || b > HP_BMAX || b > n) {
+        hp_set_error("hp_create: need 2 <= n, 1 <= b <= min(n, %d); got n=%d b=%d", HP_BMAX, n, b);
+        return 1;
+    }
+    if (!hp_device_ok()) { hp_set_error("hp_create: no CUDA device (this library has no CPU path)"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    hp_solver* s = new hp_solver();
+    int rc = hp_create_fill(s, n, b, omega_re, omega_im, cst, c_mat, c_is_device, st);
+    if (rc) { hp_destroy(s); return rc; }      // frees whatever was allocated before the failure
     *out = s;
     return 0;
 }
@@ -117,9 +124,21 @@ extern "C" int hp_precond_setup(hp_solver* s, int P, int K, int m_lo, int m_hi, 
         return 1;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    HP_CUDA(cudaMemsetAsync(s->status, 0, sizeof(int), st));       // pivot failures of the front block and of the strips
     if (hp_front_setup(s, st)) return 2;
-    if (m_lo > m_hi) { hp_free_strips(s); return 0; }     // a rank that holds no strip (front block only)
-    return hp_setup_strips(s, P, K, m_lo, m_hi, st);
+    int rc = 0;
+    if (m_lo > m_hi) hp_free_strips(s);                   // a rank that holds no strip (front block only)
+    else rc = hp_setup_strips(s, P, K, m_lo, m_hi, st);
+    if (rc) return rc;
+    int status = 0;
+    HP_CUDA(cudaMemcpyAsync(&status, s->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HP_CUDA(cudaStreamSynchronize(st));
+    if (status) {
+        hp_set_error("hp_precond_setup: a pivot vanished while factoring %s (status %d)",
+                     (status & 8) ? "the front block" : "the strips", status);
+        return 3;
+    }
+    return 0;
 }
 
 // developer hook: per-phase cycle counters of the sweep kernel.  on=1 allocates/zeroes, read copies [G][8] to host

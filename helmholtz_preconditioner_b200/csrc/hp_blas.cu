@@ -2,8 +2,8 @@
 // x += y @ V; scipy/sparse/linalg/_isolve/iterative.py as called from /root/reference/code.py:516).
 //
 // Reductions are single-launch and deterministic: every CTA reduces a fixed slice with warp shuffles and
-// writes one partial; the CTA that draws the last ticket sums the partials in index order.  All calls of
-// one process are expected on one stream (they share the partial buffer).
+// writes one partial; the CTA that draws the last ticket sums the partials in index order.  The partial buffer
+// belongs to the (device, stream) pair of the call.
 #include "hp_internal.cuh"
 
 #include <stdlib.h>
@@ -11,15 +11,30 @@
 #define HP_RED_THREADS 256
 #define HP_RED_MAX_CTAS 1184   // 8 per SM on a 148-SM part
 
-static cplx* g_partials = nullptr;
-static unsigned int* g_ticket = nullptr;
+// Reduction scratch (partials of the CTAs + the ticket): one per (device, stream).  Two reductions in flight on the same
+// stream are ordered by the stream; different streams or devices get their own buffers.
+#include <map>
+#include <mutex>
+struct HpRedScratch { cplx* partials = nullptr; unsigned int* ticket = nullptr; };
+static std::map<std::pair<int, cudaStream_t>, HpRedScratch> g_red;
+static std::mutex g_red_mu;
 
-static int hp_red_scratch() {
-    if (!g_partials) {
-        HP_CUDA(cudaMalloc(&g_partials, sizeof(cplx) * HP_RED_MAX_CTAS));
-        HP_CUDA(cudaMalloc(&g_ticket, sizeof(unsigned int)));
-        HP_CUDA(cudaMemset(g_ticket, 0, sizeof(unsigned int)));
+static int hp_red_scratch(cudaStream_t st, HpRedScratch& out) {
+    int dev = 0;
+    HP_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_red_mu);
+    auto it = g_red.find({dev, st});
+    if (it == g_red.end()) {
+        HpRedScratch r;
+        HP_CUDA(cudaMalloc(&r.partials, sizeof(cplx) * HP_RED_MAX_CTAS));
+        if (cudaMalloc(&r.ticket, sizeof(unsigned int)) != cudaSuccess || cudaMemset(r.ticket, 0, sizeof(unsigned int)) != cudaSuccess) {
+            cudaFree(r.partials); cudaFree(r.ticket);
+            hp_set_error("reduction scratch: allocation failed on device %d", dev);
+            return 2;
+        }
+        it = g_red.emplace(std::make_pair(dev, st), r).first;
     }
+    out = it->second;
     return 0;
 }
 
@@ -173,17 +188,19 @@ static unsigned hp_ew_grid(int64_t n) {
 }
 
 extern "C" int hp_dotc(int64_t n, const double* x, const double* y, double* out, void* stream) {
-    if (hp_red_scratch()) return 2;
+    HpRedScratch r;
+    if (hp_red_scratch((cudaStream_t)stream, r)) return 2;
     hp_count_launch(); hp_reduce_kernel<0><<<hp_red_grid(n), HP_RED_THREADS, 0, (cudaStream_t)stream>>>(
-        n, (const cplx*)x, (const cplx*)y, g_partials, g_ticket, (cplx*)out);
+        n, (const cplx*)x, (const cplx*)y, r.partials, r.ticket, (cplx*)out);
     HP_CUDA(cudaGetLastError());
     return 0;
 }
 
 extern "C" int hp_nrm2(int64_t n, const double* x, double* out, void* stream) {
-    if (hp_red_scratch()) return 2;
+    HpRedScratch r;
+    if (hp_red_scratch((cudaStream_t)stream, r)) return 2;
     hp_count_launch(); hp_reduce_kernel<1><<<hp_red_grid(n), HP_RED_THREADS, 0, (cudaStream_t)stream>>>(
-        n, (const cplx*)x, (const cplx*)x, g_partials, g_ticket, (cplx*)out);
+        n, (const cplx*)x, (const cplx*)x, r.partials, r.ticket, (cplx*)out);
     HP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -208,8 +225,11 @@ extern "C" int hp_scale_copy(int64_t n, double a_re, double a_im, const double* 
 }
 
 extern "C" int hp_mgs(int64_t n, int k, const double* V, int64_t ldv, double* w, double* hcol, void* stream) {
-    if (hp_red_scratch()) return 2;
     cudaStream_t st = (cudaStream_t)stream;
+    HpRedScratch r;
+    if (hp_red_scratch(st, r)) return 2;
+    cplx* const g_partials = r.partials;
+    unsigned int* const g_ticket = r.ticket;
     cplx* h = (cplx*)hcol;
     const cplx* Vc = (const cplx*)V;
     cplx* wc = (cplx*)w;

@@ -1269,7 +1269,6 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     HP_CUDA(cudaMalloc(&s->xch, sizeof(cplx) * 4 * std::max(xch_classic, xch_cluster)));
     HP_CUDA(cudaMalloc(&s->bar, sizeof(unsigned int) * (4 + L.P)));
     HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int) * (4 + L.P), st));
-    HP_CUDA(cudaMemsetAsync(s->status, 0, sizeof(int), st));
     s->m_lo = m_lo; s->m_hi = m_hi;
     s->bytes = (int64_t)pbytes;
 
@@ -1286,7 +1285,17 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     a.c = hp_ctx(s); a.lay = L; a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
     a.m_lo = m_lo; a.packets = s->packets; a.status = s->status;
     a.leaf_piped = getenv("HP_LEAF_NOPIPE") ? 0 : 1;
-    cplx* scratch = nullptr;
+    // released on every exit path
+    struct Guard {
+        hp_solver* s; cplx* scratch = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+        ~Guard() {
+            if (e0) cudaEventDestroy(e0);
+            if (e1) cudaEventDestroy(e1);
+            if (scratch && s->mleaf == scratch) s->mleaf = nullptr;     // the transfer matrices lived in the scratch
+            cudaFree(scratch);
+        }
+    } guard{s};
+    cplx*& scratch = guard.scratch;
     cplx* rowbuf = nullptr;
     HP_CUDA(cudaMalloc(&scratch, per_strip * LB));
     tr.mark("scratch allocated", st, false);
@@ -1301,8 +1310,8 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
         a.BX = p; p += sz; a.BXi = p; p += sz; a.PB = p; p += sz; a.Njj = p; p += sz;
         rowbuf = p;
     }
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    HP_CUDA(cudaEventCreate(&guard.e0)); HP_CUDA(cudaEventCreate(&guard.e1));
+    cudaEvent_t e0 = guard.e0, e1 = guard.e1;
     cudaEventRecord(e0, st);
     const int leaf_threads = ((L.QP + 31) / 32) * 32;
     const bool small_b = b <= 12;                          // thread-local b x b matrices sized 144 instead of HP_BMAX^2
@@ -1390,14 +1399,11 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     s->setup_ms = ms;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    HP_CUDA(cudaFree(scratch));
-    tr.mark("scratch freed", st, false);
-    int status = 0;
-    HP_CUDA(cudaMemcpy(&status, s->status, sizeof(int), cudaMemcpyDeviceToHost));
-    if (status) {
-        hp_set_error("hp_precond_setup: a pivot vanished while factoring the strips (status %d)", status);
-        return 3;
+    {
+        cplx* p = scratch;
+        scratch = nullptr;
+        HP_CUDA(cudaFree(p));
     }
-    return 0;
+    tr.mark("scratch freed", st, false);
+    return 0;                                              // the caller (hp_precond_setup) reads the status word
 }

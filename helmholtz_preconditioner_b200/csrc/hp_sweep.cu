@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(HP_SWEEP_THREADS) hp_sweep_kernel(HpSweepArgs 
                     ok = xtry(pc, vc) && ok;
                     if (need_v) ok = xtry(pv, vs) && ok;
                     if (ok) break;
-                    if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); break; }
+                    if (++spins > HP_SPIN_LIMIT) { hp_raise_abort(abort_flag); break; }
                     if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) break;
                 }
                 rho[e] = csub(vs, cadd(va, vc));
@@ -402,8 +402,10 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
         if (variant == 3 && !pipe_ok) variant = tma_ok ? 2 : 1;
         if (variant == 2 && !tma_ok) variant = 1;
     }
-    // the exchange ring starts all-sentinel (0xFF bytes); bar[1] = abort flag
+    // the exchange ring starts all-sentinel (0xFF bytes); bar[1] = abort flag of this launch (a timed-out launch must not
+    // stop the next one; its sticky copy bar[2] stays until the next setup)
     HP_CUDA(cudaMemsetAsync(s->xch, 0xFF, sizeof(cplx) * HP_RING * a.slot_stride, st));
+    HP_CUDA(cudaMemsetAsync(s->bar + 1, 0, sizeof(unsigned int), st));
     hp_count_launch();
     hp_profile_begin(s, st);
     if (variant == 4) {
@@ -427,10 +429,10 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
 // 0 = fine; 1 = a CTA of a sweep kernel gave up waiting for exchange data (synchronises the device)
 extern "C" int hp_sweep_status(hp_solver* s) {
     if (!s || !s->bar) return 0;
-    unsigned int v[2] = {0, 0};
+    unsigned int v[3] = {0, 0, 0};
     if (cudaDeviceSynchronize() != cudaSuccess) return 2;
     if (cudaMemcpy(v, s->bar, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 2;
-    return v[1] ? 1 : 0;
+    return (v[1] | v[2]) ? 1 : 0;
 }
 
 extern "C" int hp_sweep_forward(hp_solver* s, double* u_dev, int m_from, int m_to, void* stream) {

@@ -36,7 +36,7 @@ __device__ __forceinline__ cplx xwait(const cplx* p, unsigned int* abort_flag, v
     unsigned int spins = 0;
     while (!xtry(p, v)) {
         if (*dead) break;
-        if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; break; }
+        if (++spins > HP_SPIN_LIMIT) { hp_raise_abort(abort_flag); *dead = 1u; break; }
         if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) { *dead = 1u; break; }
     }
     return v;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                             if (need_x) ok = xtry(px, xv);
                             for (int kk = 0; kk < K; ++kk) ok = xtry(slot + a.oGP + (size_t)(g + kk) * b2 + t, gv[kk & 15]) && ok;
                             if (ok || *dead) break;
-                            if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; break; }
+                            if (++spins > HP_SPIN_LIMIT) { hp_raise_abort(abort_flag); *dead = 1u; break; }
                             if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) { *dead = 1u; break; }
                         }
                         xlr_c[t] = xv;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(HP2_THREADS) hp_sweep2_kernel(HpSweepArgs a) {
                             if (need_v[i]) ok = xtry(pv[i], vs[i]) && ok;
                         }
                         if (ok || *dead) break;
-                        if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; break; }
+                        if (++spins > HP_SPIN_LIMIT) { hp_raise_abort(abort_flag); *dead = 1u; break; }
                         if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) { *dead = 1u; break; }
                     }
 #pragma unroll

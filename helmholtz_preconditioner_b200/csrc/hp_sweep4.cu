@@ -28,6 +28,7 @@
 #include "hp_sweep4.h"
 
 #include <stdlib.h>
+#include <string.h>
 
 #define HP4_CRIT 96          // critical group: warps 0-2
 #define HP4_PROD 32          // warp 3: issues every TMA copy (its lane 0), driven by the empty barriers of the rings
@@ -70,7 +71,7 @@ __device__ __noinline__ void mbar_wait4_slow(unsigned long long* bar, unsigned i
 #pragma unroll 1
     while (!mbar_try_cluster(bar, parity)) {
         if (*dead) break;
-        if (++spins > (1u << 20)) { atomicExch(abort_flag, 1u); *dead = 1u; break; }
+        if (++spins > (1u << 20)) { hp_raise_abort(abort_flag); *dead = 1u; break; }
         if ((spins & 0x3FF) == 0 && *((volatile unsigned int*)abort_flag)) { *dead = 1u; break; }
     }
 }
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                                 val[o][pp] = cmake(__longlong_as_double((long long)lo[o][pp]), __longlong_as_double((long long)hi[o][pp]));
                             }
                         if (__all_sync(0xffffffffu, ok || *dead)) break;
-                        if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; }
+                        if (++spins > HP_SPIN_LIMIT) { hp_raise_abort(abort_flag); *dead = 1u; }
                         if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) *dead = 1u;
                     }
                     HP_TICK(4);
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
 #pragma unroll
                         for (int u = 0; u < HP4_PW; ++u) ok = ok && xvalid(lo[u], hi[u]);
                         if (__all_sync(0xffffffffu, ok || *dead)) break;
-                        if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); *dead = 1u; }
+                        if (++spins > HP_SPIN_LIMIT) { hp_raise_abort(abort_flag); *dead = 1u; }
                         if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) *dead = 1u;
                     }
 #pragma unroll
@@ -732,6 +733,31 @@ int hp_sweep4_max_clusters(const HpLayout& L, int b) {
     return ncl;
 }
 
+// a CUDA profiler / injection library is attached to this process: Nsight Compute's environment, or one of its
+// injection libraries mapped into the process
+extern char** environ;
+static bool hp_profiler_attached() {
+    static int cached = -1;
+    if (cached < 0) {
+        int found = 0;
+        for (char** e = environ; e && *e; ++e)
+            if (!strncmp(*e, "CUDA_INJECTION64_PATH=", 22) || !strncmp(*e, "NV_COMPUTE_PROFILER_", 20) ||
+                !strncmp(*e, "NV_NSIGHT_INJECTION_", 20) || !strncmp(*e, "NSIGHT_CUDA_DEBUGGER=", 21))
+                found = 1;
+        if (!found) {
+            if (FILE* f = fopen("/proc/self/maps", "r")) {
+                char line[1024];
+                while (!found && fgets(line, sizeof(line), f))
+                    if (strstr(line, "nsight-compute") || strstr(line, "libcuda-injection") || strstr(line, "libInterceptorInjection") ||
+                        strstr(line, "libTreeLauncher")) found = 1;
+                fclose(f);
+            }
+        }
+        cached = found;
+    }
+    return cached == 1;
+}
+
 int hp_sweep4_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st) {
     const HpLayout& L = s->lay;
     int dev = 0, max_smem = 0;
@@ -751,13 +777,17 @@ int hp_sweep4_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st) {
     at[1].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 2;
     void* args[] = {&a, &pl};
-    // cooperative = the driver checks that all clusters are co-resident; profilers that replay the kernel refuse that
-    // combination, so a refused launch is repeated as a plain cluster launch (co-residency was checked at setup)
-    cudaError_t e = getenv("HP_NO_COOP") ? cudaErrorNotSupported : cudaLaunchKernelExC(&cfg, fn, args);
+    // cooperative = the driver checks that all clusters are co-resident (the CTAs exchange data by spinning on L2 words
+    // and mbarriers).  Kernel-replaying profilers (ncu) refuse cooperative cluster launches, so under a profiler - and with
+    // HP_NO_COOP - the plain cluster launch is taken up front: co-residency was checked against
+    // cudaOccupancyMaxActiveClusters when the partition was chosen.  Any other failure is an error.
+    if (hp_profiler_attached() || getenv("HP_NO_COOP")) cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        cfg.numAttrs = 1;
-        HP_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+        hp_set_error("sweep: %s cluster launch of %d CTAs failed: %s", cfg.numAttrs == 2 ? "cooperative" : "plain", L.G,
+                     cudaGetErrorString(e));
+        return 2;
     }
     return 0;
 }

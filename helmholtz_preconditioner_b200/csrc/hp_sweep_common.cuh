@@ -19,7 +19,8 @@ struct HpSweepArgs {
     cplx* yout;
     cplx* xch;                // exchange ring: HP_RING slots of slot_stride complex numbers
     size_t oGP, oGR, oXS, oVS, slot_stride;      // (cluster kernel: oXS = partial x [P-1][K*NRQ], oGP = gf partials [P][K][b])
-    unsigned int* bar;        // [1] abort flag (a spin ran into HP_SPIN_LIMIT)
+    unsigned int* bar;        // [1] abort flag of the running launch (a spin ran into HP_SPIN_LIMIT), cleared before every launch;
+                              // [2] sticky copy, cleared by the setup only (hp_sweep_status, checked on the product path)
     const cplx *s2t, *is1t;
     double ih2;
     long long* dbg;           // optional [G][8] per-phase cycle sums (thread 0 of every CTA), NULL = off
@@ -50,12 +51,17 @@ __device__ __forceinline__ void xload(const cplx* p, unsigned long long& lo, uns
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
 }
 __device__ __forceinline__ bool xvalid(unsigned long long lo, unsigned long long hi) { return lo != HP_SENTINEL && hi != HP_SENTINEL; }
+// a runaway wait: stop this launch (flag [0]) and leave a mark that survives it (flag [1], read by hp_sweep_status)
+__device__ __forceinline__ void hp_raise_abort(unsigned int* abort_flag) {
+    atomicExch(abort_flag + 1, 1u);
+    hp_raise_abort(abort_flag);
+}
 // spin until the word is valid; on a runaway spin raise the abort flag (the kernel then terminates)
 __device__ __forceinline__ cplx xget(const cplx* p, unsigned int* abort_flag) {
     cplx v;
     unsigned int spins = 0;
     while (!xtry(p, v)) {
-        if (++spins > HP_SPIN_LIMIT) { atomicExch(abort_flag, 1u); break; }
+        if (++spins > HP_SPIN_LIMIT) { hp_raise_abort(abort_flag); break; }
         if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) break;
     }
     return v;

@@ -45,10 +45,15 @@ def lartg(f, g):
 class DeviceVectors:
     """Krylov vector kernels on (a slab of) the field; reductions are summed over `group` if given."""
 
-    def __init__(self, nloc, device, group=None):
+    def __init__(self, nloc, device, group=None, restart=20):
         self.lib = _lib.require_device()
-        self.nloc, self.device, self.group = nloc, device, group
-        self.scal = torch.zeros(64, dtype=torch.complex128, device=device)
+        self.nloc, self.device, self.group = nloc, torch.device(device), group
+        self.scal = torch.zeros(max(64, restart + 3), dtype=torch.complex128, device=device)
+
+    def reserve(self, restart):
+        """hp_mgs writes restart + 2 scalars (coefficients, norm after, norm before)"""
+        if self.scal.numel() < restart + 3:
+            self.scal = torch.zeros(restart + 3, dtype=torch.complex128, device=self.device)
 
     def _reduce(self, t):
         if self.group is not None:
@@ -99,14 +104,15 @@ class DeviceVectors:
                    "hp_combine")
 
 
-def gmres(matvec, psolve, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None, callback=None, nglobal=None):
+def gmres(matvec, psolve, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None, callback=None, nglobal=None,
+          health=None):
     """scipy.sparse.linalg.gmres(A, b, M=M, rtol=..., restart=..., maxiter=..., callback=...) on device vectors.
 
     matvec(x, out), psolve(x, out): device operators writing into `out`.  b: device vector (local slab).
     Returns (x, info, hist): hist holds what scipy hands to the legacy callback, one entry per inner iteration.
     """
     gen = gmres_steps(matvec, b, vec=vec, rtol=rtol, atol=atol, restart=restart, maxiter=maxiter, callback=callback,
-                      nglobal=nglobal)
+                      nglobal=nglobal, health=health)
     try:
         req = next(gen)
         while True:
@@ -140,9 +146,11 @@ def gmres_batch(matvec, psolve_batch, bs, *, vec, **kw):
     return results
 
 
-def gmres_steps(matvec, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None, callback=None, nglobal=None):
+def gmres_steps(matvec, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None, callback=None, nglobal=None,
+                health=None):
     """Generator form of gmres(): yields (x, out) whenever the preconditioner has to be applied (out = M x) and
-    returns (x, info, hist) through StopIteration."""
+    returns (x, info, hist) through StopIteration.  health(): called at every restart boundary (the host is in sync
+    with the device there anyway); raises if a kernel of the operators reported a fault."""
     nloc = b.numel()
     n = nglobal if nglobal is not None else nloc
     dev = b.device
@@ -156,6 +164,7 @@ def gmres_steps(matvec, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None
     if maxiter is None:
         maxiter = n * 10
     restart = min(restart, n)
+    vec.reserve(restart)
     V = torch.empty((restart + 1, nloc), dtype=torch.complex128, device=dev)
     r = torch.empty_like(b)
     av = torch.empty_like(b)
@@ -227,6 +236,8 @@ def gmres_steps(matvec, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None
         vec.scale_copy(-1.0, av, r)
         vec.axpy(1.0, b, r)
         rnorm = vec.norm(r)
+        if health is not None:
+            health()
         if inner_iter == maxiter:
             return x, (0 if rnorm <= atol else maxiter), hist
         if rnorm <= atol:

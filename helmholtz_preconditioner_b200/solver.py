@@ -49,6 +49,8 @@ class HelmholtzSolver:
     def __init__(self, n, b, omega, const, c_mat, device=None):
         self.lib = _lib.require_device()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.index is None:
+            self.device = torch.device(f"cuda:{torch.cuda.current_device()}")
         self.n, self.b, self.omega, self.const = int(n), int(b), complex(omega), float(const)
         self.h = 1 / (n + 1)
         self.eta = b * self.h
@@ -82,6 +84,7 @@ class HelmholtzSolver:
     # ---- operator -------------------------------------------------------------------------------------
     def assemble_csr(self):
         """build_A_matrix: sorted CSR on the device (int32 indices, complex128 values)."""
+        self._on_device()
         n = self.n
         N = n * n
         nnz = self.lib.hp_csr_nnz(n)
@@ -94,6 +97,7 @@ class HelmholtzSolver:
 
     def matvec(self, x, out=None):
         """y = A x, matrix free."""
+        self._on_device()
         if out is None:
             out = torch.empty_like(x)
         _lib.check(self.lib.hp_stencil_matvec(self.handle, _ptr(x), _ptr(out), _stream()), "hp_stencil_matvec")
@@ -108,6 +112,7 @@ class HelmholtzSolver:
     def setup_preconditioner(self, P=0, K=0, m_lo=0, m_hi=0, layout="auto"):
         """algo2_3.  (m_lo, m_hi) = (0, 0): all strips b+1..n; otherwise the strips of this rank's slab.
         layout: "auto" (cluster when a partition exists), "classic", "cluster" (include/helmholtz_b200.h)."""
+        self._on_device()
         _lib.check(self.lib.hp_set_layout_mode(self.handle, LAYOUT_MODES[layout]), "hp_set_layout_mode")
         _lib.check(self.lib.hp_precond_setup(self.handle, P, K, m_lo, m_hi, _stream()), "hp_precond_setup")
         if m_lo == 0 and m_hi == 0:
@@ -123,6 +128,23 @@ class HelmholtzSolver:
     def sweep_status(self):
         """0 = fine (synchronises the device)."""
         return int(self.lib.hp_sweep_status(self.handle))
+
+    def check_status(self):
+        """Raise if a sweep kernel gave up waiting for another CTA since the setup (its output is then garbage).
+        Synchronises the device; called where the host waits for the device anyway (GMRES restart boundaries, the end
+        of run_solver, algo2_4)."""
+        st = self.sweep_status()
+        if st:
+            raise _lib.HelmholtzB200Error(
+                f"sweep kernel fault (status {st}): a CTA timed out waiting for exchange data; results since the last "
+                "setup_preconditioner() are invalid")
+
+    def _on_device(self):
+        """every call runs on the current device and stream: refuse a solver that lives elsewhere"""
+        if torch.cuda.current_device() != self.device.index:
+            raise _lib.HelmholtzB200Error(
+                f"solver lives on {self.device}, current device is cuda:{torch.cuda.current_device()} "
+                "(wrap the call in torch.cuda.device(solver.device))")
 
     @property
     def precond_bytes(self):
@@ -157,6 +179,7 @@ class HelmholtzSolver:
 
     def strip_apply(self, m, v, out=None):
         """T_m v: last n entries of H_m^{-1} [0; v]  (code.py:368-370)."""
+        self._on_device()
         if out is None:
             out = torch.empty_like(v)
         _lib.check(self.lib.hp_strip_apply(self.handle, m, _ptr(v), _ptr(out), _stream()), "hp_strip_apply")
@@ -164,6 +187,7 @@ class HelmholtzSolver:
 
     def precond_apply(self, f, out=None, diag="reference"):
         """algo2_4: out = M f."""
+        self._on_device()
         if out is None:
             out = torch.empty_like(f)
         _lib.check(self.lib.hp_precond_apply(self.handle, _ptr(f), _ptr(out), DIAG_MODES[diag], _stream()),
@@ -260,7 +284,9 @@ def algo2_4(f_vec, b, n, lu_HF, A_b1F=None, A_Fb1=None, up_A_ra=None, lo_A_ra=No
     implied by the solver handle and ignored.  Returns M f as an (n, n) device tensor like the reference's u."""
     s = lu_HF
     f = _as_device_field(f_vec, s.device)
-    return s.precond_apply(f, diag=diag).reshape(n, n)
+    u = s.precond_apply(f, diag=diag).reshape(n, n)
+    s.check_status()
+    return u
 
 
 @dataclass
@@ -299,7 +325,7 @@ def run_solver(n, b, wave_num, const, alpha, init_func=fields.init_c1_f1, plot_s
         s.setup_preconditioner(P, K)                     # algo2_3, code.py:496
     torch.cuda.synchronize(s.device)
     t1 = time.time()
-    vec = DeviceVectors(n * n, s.device)
+    vec = DeviceVectors(n * n, s.device, restart=restart)
     Mf = None
     if precond_input == "rhs":
         Mf = s.precond_apply(f, diag=diag)
@@ -314,8 +340,8 @@ def run_solver(n, b, wave_num, const, alpha, init_func=fields.init_c1_f1, plot_s
     else:
         raise ValueError("precond_input must be 'rhs' or 'vector'")
     u, info, hist = gmres(lambda x, out: s.matvec(x, out), psolve, f, vec=vec, rtol=rtol, restart=restart,
-                          maxiter=maxiter)
-    torch.cuda.synchronize(s.device)
+                          maxiter=maxiter, health=s.check_status)
+    s.check_status()
     t2 = time.time()
     if verbose:
         print("GMRES iterations with preconditioner: " + str(len(hist)))      # code.py:520
