@@ -32,6 +32,7 @@ SIGNATURES = {
     "hp_sweep_status": (_i, [_vp]),
     "hp_set_sweep_variant": (_i, [_vp, _i]),
     "hp_set_layout_mode": (_i, [_vp, _i]),
+    "hp_set_front_mode": (_i, [_vp, _i]),
     "hp_strip_layout_ex": (_i, [_vp, _ip, _ip, _ip, _ip]),
     "hp_precond_bytes": (_i64, [_vp]),
     "hp_precond_setup_ms": (_d, [_vp]),

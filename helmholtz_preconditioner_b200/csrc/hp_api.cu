@@ -111,6 +111,7 @@ extern "C" int hp_destroy(hp_solver* s) {
     cudaFree(s->s1t); cudaFree(s->is1t); cudaFree(s->s2t); cudaFree(s->is2t);
     cudaFree(s->c_mat); cudaFree(s->kappa); cudaFree(s->status);
     cudaFree(s->f_low); cudaFree(s->f_invd); cudaFree(s->f_up); cudaFree(s->TF);
+    hp_front_coupled_free(s);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     delete s;
     return 0;
@@ -148,6 +149,12 @@ extern "C" int hp_debug_phases(hp_solver* s, int on, long long* out_host) {
     if (on && !s->dbg) { HP_CUDA(cudaMalloc(&s->dbg, sz)); HP_CUDA(cudaMemset(s->dbg, 0, sz)); }
     if (out_host && s->dbg) HP_CUDA(cudaMemcpy(out_host, s->dbg, sz, cudaMemcpyDeviceToHost));
     if (!on && s->dbg) { cudaFree(s->dbg); s->dbg = nullptr; }
+    return 0;
+}
+// front block used by the next hp_precond_setup: 0 = block diagonal (the reference's get_A_FF_block), 1 = coupled
+extern "C" int hp_set_front_mode(hp_solver* s, int mode) {
+    if (!s || mode < 0 || mode > 1) { hp_set_error("hp_set_front_mode: mode must be 0 or 1"); return 1; }
+    s->front_mode = mode;
     return 0;
 }
 // sweep kernel: 0 = automatic; classic layout: 1 direct, 2 TMA staged, 3 pipelined; cluster layout: 4

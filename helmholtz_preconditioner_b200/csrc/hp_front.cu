@@ -241,6 +241,8 @@ int hp_front_setup(hp_solver* s, cudaStream_t st) {
     hp_count_launch(); hp_front_factor_kernel<<<1, 32, 0, st>>>(s->n, s->b, ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa,
                                              s->f_low, s->f_invd, s->f_up, s->status);
     HP_CUDA(cudaGetLastError());
+    if (s->front_mode == 1) return hp_front_coupled_setup(s, st);
+    hp_front_coupled_free(s);
     return 0;
 }
 
@@ -250,11 +252,15 @@ extern "C" int hp_front_begin(hp_solver* s, double* u_dev, void* stream) {
     const int n = s->n, b = s->b;
     cplx* u = (cplx*)u_dev;
     cplx* work = s->TF + (size_t)b * n;
-    hp_count_launch();
-    if (n <= HP_FS_THREADS * HP_FS_EMAX)
+    if (s->front_mode == 1) {
+        if (hp_front_coupled_solve(s, 0, 0, u, s->TF, nullptr, cmake(0, 0), st)) return 2;
+    } else if (n <= HP_FS_THREADS * HP_FS_EMAX) {
+        hp_count_launch();
         hp_front_scan_kernel<<<b, HP_FS_THREADS, 0, st>>>(n, b, 0, 0, s->f_low, s->f_invd, s->f_up, u, s->TF, nullptr, cmake(0, 0), s->is1t);
-    else
+    } else {
+        hp_count_launch();
         hp_front_solve_kernel<<<1, 32, 0, st>>>(n, b, 0, b, 0, s->f_low, s->f_invd, s->f_up, u, s->TF, nullptr, cmake(0, 0), s->is1t, work);
+    }
     if (b < n) {
         // u_{b+1} -= A_{b+1,b} (T_F u_F)_b : A_{b+1,b} = diag(c3) of grid row b+1 (code.py:145-154, :365)
         double ih2 = 1.0 / (s->pml.h * s->pml.h);
@@ -272,6 +278,16 @@ extern "C" int hp_front_end(hp_solver* s, double* u_dev, void* stream) {
     const int n = s->n, b = s->b;
     cplx* u = (cplx*)u_dev;
     cplx* work = s->TF + (size_t)b * n;
+    if (s->front_mode == 1) {
+        // u_F = T_F u_F - H_F^{-1} [0; A_{b,b+1} u_{b+1}] with the full H_F: every row of u_F changes
+        if (b < n) {
+            double ih2 = 1.0 / (s->pml.h * s->pml.h);
+            cplx fac = cscale(ih2, s->s2t_h[2 * b + 1]);
+            return hp_front_coupled_solve(s, 2, 2, u + (size_t)b * n, u, s->TF, fac, st);
+        }
+        HP_CUDA(cudaMemcpyAsync(u, s->TF, sizeof(cplx) * (size_t)b * n, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
     if (b > 1) HP_CUDA(cudaMemcpyAsync(u, s->TF, sizeof(cplx) * (size_t)(b - 1) * n, cudaMemcpyDeviceToDevice, st));
     if (b < n) {
         // u_b = (T_F u_F)_b - Tri_b^{-1} (A_{b,b+1} u_{b+1}) : A_{b,b+1} = diag(c4) of grid row b (code.py:131-140)

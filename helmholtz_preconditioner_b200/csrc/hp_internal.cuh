@@ -68,6 +68,13 @@ struct hp_solver {
     // front block: Thomas factors of the b tridiagonal diagonal blocks (reference H_F)
     cplx *f_low = nullptr, *f_invd = nullptr, *f_up = nullptr;   // [b][n]
     cplx* TF = nullptr;                                           // [b][n]   T_F u_F kept between the stages
+    // coupled front block (csrc/hp_front_coupled.cu): H_F = A[:bn, :bn] with the couplings between the rows kept
+    int front_mode = 0;           // 0 = block diagonal (reference, code.py:178-183), 1 = coupled (the paper's A_FF)
+    int fc_P = 0, fc_QP = 0;      // leaves of the x1 partition, widest leaf
+    int *fc_leaf_start = nullptr, *fc_leaf_q = nullptr, *fc_sep = nullptr;
+    cplx *fc_Sinv = nullptr, *fc_LU = nullptr;                    // [n][b*b] leaf Schur chains, [n][2][b] x1 couplings
+    cplx *fc_T = nullptr, *fc_Sl = nullptr, *fc_Su = nullptr;     // [P-1][b*b] separator chain and off-diagonal blocks
+    cplx* fc_work = nullptr;                                      // [b][n] first-pass leaf solutions
     // sweep scratch
     cplx* xch = nullptr;          // exchange ring of the sweep kernel (csrc/hp_sweep.cu)
     long long* dbg = nullptr;     // optional per-phase cycle counters of the sweep kernel [G][8]
@@ -96,6 +103,12 @@ int hp_setup_strips(hp_solver* s, int P, int K, int m_lo, int m_hi, cudaStream_t
 void hp_free_strips(hp_solver* s);
 // hp_front.cu
 int hp_front_setup(hp_solver* s, cudaStream_t st);
+// hp_front_coupled.cu : out = H_F^-1 rhs (out_mode 0) or base - H_F^-1 rhs (out_mode 2) on b field rows;
+// rhs_mode 0: rhs = the b rows at `in`; 2: rhs = [0; ..; 0; fac * is1t ⊙ in] (one row at `in`)
+int hp_front_coupled_setup(hp_solver* s, cudaStream_t st);
+void hp_front_coupled_free(hp_solver* s);
+int hp_front_coupled_solve(hp_solver* s, int rhs_mode, int out_mode, const cplx* in, cplx* out, const cplx* base, cplx fac,
+                           cudaStream_t st);
 // hp_sweep.cu : mode 0 = forward, 1 = backward, 2 = single strip apply (vin -> yout)
 int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout, int m_from, int m_to,
                     int diag_mode, cudaStream_t st);

@@ -22,6 +22,7 @@ from .gmres import DeviceVectors, gmres
 
 DIAG_MODES = {"reference": 0, "paper": 1}
 LAYOUT_MODES = {"auto": 0, "classic": 1, "cluster": 2}
+FRONT_MODES = {"blockdiag": 0, "coupled": 1}
 
 
 def _ptr(t):
@@ -109,10 +110,14 @@ class HelmholtzSolver:
         return out
 
     # ---- preconditioner -------------------------------------------------------------------------------
-    def setup_preconditioner(self, P=0, K=0, m_lo=0, m_hi=0, layout="auto"):
+    def setup_preconditioner(self, P=0, K=0, m_lo=0, m_hi=0, layout="auto", front="blockdiag"):
         """algo2_3.  (m_lo, m_hi) = (0, 0): all strips b+1..n; otherwise the strips of this rank's slab.
-        layout: "auto" (cluster when a partition exists), "classic", "cluster" (include/helmholtz_b200.h)."""
+        layout: "auto" (cluster when a partition exists), "classic", "cluster" (include/helmholtz_b200.h).
+        front: "blockdiag" = the reference's H_F (code.py:178-183, only the diagonal blocks), "coupled" = the full
+        A[:bn, :bn] of the paper (2-5 GMRES iterations instead of 70-200 with diag='paper')."""
         self._on_device()
+        _lib.check(self.lib.hp_set_front_mode(self.handle, FRONT_MODES[front]), "hp_set_front_mode")
+        self.front = front
         _lib.check(self.lib.hp_set_layout_mode(self.handle, LAYOUT_MODES[layout]), "hp_set_layout_mode")
         _lib.check(self.lib.hp_precond_setup(self.handle, P, K, m_lo, m_hi, _stream()), "hp_precond_setup")
         if m_lo == 0 and m_hi == 0:
@@ -273,9 +278,9 @@ def build_A_matrix(b, const, eta, omega, h, n, c_mat, device=None):
     return _solver_for(b, const, eta, omega, h, n, c_mat, device).assemble_csr()
 
 
-def algo2_3(b, const, eta, omega, h, n, c_mat, device=None, P=0, K=0, layout="auto"):
+def algo2_3(b, const, eta, omega, h, n, c_mat, device=None, P=0, K=0, layout="auto", front="blockdiag"):
     """code.py:345-353.  Returns (lu_HF, lu_Hm_ra): both are the same factorisation handle here."""
-    s = _solver_for(b, const, eta, omega, h, n, c_mat, device).setup_preconditioner(P, K, layout=layout)
+    s = _solver_for(b, const, eta, omega, h, n, c_mat, device).setup_preconditioner(P, K, layout=layout, front=front)
     return s, s
 
 
@@ -304,13 +309,16 @@ class SolveResult:
 
 
 def run_solver(n, b, wave_num, const, alpha, init_func=fields.init_c1_f1, plot_solution=False, *, c_mat=None,
-               f_mat=None, diag="reference", precond_input="rhs", rtol=1e-3, restart=20, maxiter=None, device=None,
-               P=0, K=0, verbose=True, solver=None):
+               f_mat=None, diag="reference", precond_input="rhs", front="blockdiag", rtol=1e-3, restart=20, maxiter=None,
+               device=None, P=0, K=0, verbose=True, solver=None):
     """code.py:424-541 (the preconditioned solve; plotting is not part of this package).
 
     precond_input='rhs' is the reference as written: its LinearOperator ignores the vector it is given and
     always returns algo2_4(f_vec) (code.py:510-511).  'vector' applies the preconditioner to the argument.
     diag='reference' keeps u_m <- u_m - T_m u_m (code.py:372-375); 'paper' is Engquist-Ying's u_m <- T_m u_m.
+    front='blockdiag' is the reference's H_F (code.py:178-183); 'coupled' keeps the couplings between its rows.
+    The reference as written (rhs / reference / blockdiag) does not converge (info != 0); vector / paper converges,
+    with front='coupled' in a handful of iterations.  A solver passed in keeps the front block it was set up with.
     """
     lib = _lib.require_device()   # noqa: F841  (fail before any host work if the device path is missing)
     t0 = time.time()
@@ -322,7 +330,7 @@ def run_solver(n, b, wave_num, const, alpha, init_func=fields.init_c1_f1, plot_s
     s = solver if solver is not None else HelmholtzSolver(n, b, omega, const, c_mat, device=device)
     f = _as_device_field(f_mat, s.device)                # f_mat.flatten(), code.py:448
     if solver is None:
-        s.setup_preconditioner(P, K)                     # algo2_3, code.py:496
+        s.setup_preconditioner(P, K, front=front)        # algo2_3, code.py:496
     torch.cuda.synchronize(s.device)
     t1 = time.time()
     vec = DeviceVectors(n * n, s.device, restart=restart)

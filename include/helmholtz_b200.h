@@ -72,6 +72,10 @@ double hp_precond_setup_ms(hp_solver* s);
  * (one CTA per leaf part, N distributed by rows), 2 = cluster (a leaf is a thread-block cluster of K <= 8 CTAs, N
  * distributed by separator columns; fails when no such partition fits) */
 int hp_set_layout_mode(hp_solver* s, int mode);
+/* front block H_F factored by the next hp_precond_setup (algo2_3, code.py:346-347): 0 = the reference's
+ * get_A_FF_block (code.py:178-183: only the b diagonal blocks A_11..A_bb, b independent tridiagonal systems), 1 = the
+ * coupled block A[:bn, :bn] of Engquist & Ying's Algorithm 2.3/2.4, i.e. get_Hm(b) (code.py:283-290) solved in full */
+int hp_set_front_mode(hp_solver* s, int mode);
 /* sweep kernel variant: 0 = automatic; classic layout: 1 = direct loads, 2 = TMA-staged block-synchronous,
  * 3 = pipelined with two hand-overs through L2 per strip; cluster layout: 4 = one hand-over through L2 per strip, the
  * exchanges inside a leaf through distributed shared memory */

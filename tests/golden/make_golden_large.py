@@ -157,7 +157,7 @@ def part_ref(case):
             compact(f"orc_{front}_{diag}_Mf", of, n, b, out)
             compact(f"orc_{front}_{diag}_Mx", ox, n, b, out)
         del P
-    save(case, "ref", out)
+    return out
 
 
 def part_gmres(case, part):
@@ -178,7 +178,7 @@ def part_gmres(case, part):
                true_residual=np.linalg.norm(fv - A @ u) / np.linalg.norm(fv), oracle_seconds=dt)
     compact("u", u, n, b, out)
     print(case, part, "niter", niter, "info", info, "true residual", out["true_residual"], f"{dt:.0f} s", flush=True)
-    save(case, part, out)
+    return out
 
 
 def part_mf_streamed(case):
@@ -244,16 +244,20 @@ def part_mf_streamed(case):
         u[:b] = (TF[fi][k] - luF[fi].solve(Au)).reshape(b, n)
         compact(f"orc_{fronts[fi]}_{d}_{'Mf' if k == 0 else 'Mx'}", u.ravel(), n, b, out)
     out["oracle_seconds"] = time.time() - t0
-    save(case, "mf", out)
+    return out
 
 
-def run(case, part):
+def compute(case, part):
     if case == "D":
         assert part == "mf"
         return part_mf_streamed(case)
     if part == "ref":
         return part_ref(case)
     return part_gmres(case, part)
+
+
+def run(case, part):
+    save(case, part, compute(case, part))
 
 
 if __name__ == "__main__":

@@ -113,3 +113,43 @@ def test_gmres_restatement_matches_scipy():
     assert info == info2 and len(hist) == len(hist2)
     assert np.allclose(hist, hist2, rtol=1e-6)
     assert relerr(x2, x) < 1e-10
+
+
+# ---- large fixtures (tests/golden/make_golden_large.py) -------------------------------------------------------------
+LARGE = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "large_*.npz")))
+
+
+def test_large_fixtures_present_and_consistent():
+    """every production-size case has its reference part and its converged GMRES parts; stored metadata is coherent"""
+    names = {os.path.basename(p) for p in LARGE}
+    for stem in ("large_n63_b12_c1f1", "large_n511_b12_c1f1", "large_n1023_b12_c1f1", "large_n1024_b20_const"):
+        for part in ("ref", "pb", "pc", "rb", "rc"):
+            assert f"{stem}__{part}.npz" in names, f"{stem}__{part}.npz missing"
+    for p in LARGE:
+        g = np.load(p)
+        n = int(g["n"])
+        assert g["z"].shape == (n,) and g["z2"].shape == (n,)
+        if "hist" in g.files:
+            assert len(g["hist"]) == int(g["niter"])
+            if str(g["diag"]) == "paper":
+                assert int(g["info"]) == 0 and float(g["true_residual"]) <= 1e-3       # converged solves
+            else:                                                                      # code.py:372-375 as written
+                assert int(g["info"]) in (0, int(g["maxiter"]))
+                if str(g["front"]) == "blockdiag":
+                    assert int(g["info"]) == int(g["maxiter"])                         # the reference's M: never converges
+        if "oracle_vs_reference" in g.files:
+            assert np.all(g["oracle_vs_reference"] < 1e-13)                            # oracle == unmodified reference
+
+
+@pytest.mark.parametrize("part", ["pb", "pc", "rb"])
+def test_large_generator_reproduces_small_case(part):
+    """the committed generator, run again on the small case T, reproduces the committed fixture"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_large", os.path.join(os.path.dirname(__file__), "golden", "make_golden_large.py"))
+    mgl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgl)
+    out = mgl.compute("T", part)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"large_n63_b12_c1f1__{part}.npz"))
+    assert int(out["niter"]) == int(g["niter"]) and int(out["info"]) == int(g["info"])
+    assert np.allclose(out["hist"], g["hist"], rtol=1e-9, atol=0)
+    assert relerr(out["u_rows"], g["u_rows"]) < 1e-9 and relerr(out["u_rowsum"], g["u_rowsum"]) < 1e-9
