@@ -33,6 +33,7 @@ SIGNATURES = {
     "hp_set_sweep_variant": (_i, [_vp, _i]),
     "hp_set_layout_mode": (_i, [_vp, _i]),
     "hp_set_front_mode": (_i, [_vp, _i]),
+    "hp_precond_set_front": (_i, [_vp, _i, _vp]),
     "hp_strip_layout_ex": (_i, [_vp, _ip, _ip, _ip, _ip]),
     "hp_precond_bytes": (_i64, [_vp]),
     "hp_precond_setup_ms": (_d, [_vp]),
@@ -51,6 +52,7 @@ SIGNATURES = {
     "hp_axpy_dev": (_i, [_i64, _vp, _d, _vp, _vp, _vp]),
     "hp_scale_copy": (_i, [_i64, _d, _d, _vp, _vp, _vp]),
     "hp_mgs": (_i, [_i64, _i, _vp, _i64, _vp, _vp, _vp]),
+    "hp_mgs_step": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_combine": (_i, [_i64, _i, _vp, _i64, _vp, _vp, _vp]),
 }
 

@@ -157,6 +157,18 @@ extern "C" int hp_set_front_mode(hp_solver* s, int mode) {
     s->front_mode = mode;
     return 0;
 }
+// re-factor the front block alone with another mode; the strip factorisation is kept
+extern "C" int hp_precond_set_front(hp_solver* s, int mode, void* stream) {
+    if (hp_set_front_mode(s, mode)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    HP_CUDA(cudaMemsetAsync(s->status, 0, sizeof(int), st));
+    if (hp_front_setup(s, st)) return 2;
+    int status = 0;
+    HP_CUDA(cudaMemcpyAsync(&status, s->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HP_CUDA(cudaStreamSynchronize(st));
+    if (status) { hp_set_error("hp_precond_set_front: a pivot vanished while factoring the front block (status %d)", status); return 3; }
+    return 0;
+}
 // sweep kernel: 0 = automatic; classic layout: 1 direct, 2 TMA staged, 3 pipelined; cluster layout: 4
 extern "C" int hp_set_sweep_variant(hp_solver* s, int v) { if (!s) return 1; s->sweep_variant = v; return 0; }
 // generator layout chosen by the next hp_precond_setup: 0 = automatic, 1 = classic (G = P*K CTAs, N by rows),

@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(HP_RED_THREADS) hp_reduce_kernel(int64_t n, co
 }
 
 // Fused Gram-Schmidt step: w -= h v (h read from device memory) and, in the same pass, the reduction the next step needs
-// from the updated w: MODE 0 out = conj(vn) . w (the next coefficient), MODE 1 out = ||w|| (after the last vector).
+// from the updated w: MODE 0 out = conj(vn) . w (the next coefficient), MODE 1 out = ||w|| (after the last vector),
+// MODE 2 out = sum |w|^2 (distributed vectors: the square root is taken after the all-reduce).
 // Same grid, same slices and the same accumulation order as hp_reduce_kernel, so the results are bit-identical to the
 // separate axpy and reduction (4 passes over n-vectors instead of 5).
 template <int MODE>
@@ -251,6 +252,23 @@ extern "C" int hp_mgs(int64_t n, int k, const double* V, int64_t ldv, double* w,
         hp_count_launch(); hp_axpy_reduce_kernel<1><<<g, HP_RED_THREADS, 0, st>>>(n, h + k - 1, Vc + (size_t)(k - 1) * ldv, wc, wc, g_partials, g_ticket,
                                                                           h + k);                                     // h1
     }
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// one fused Gram-Schmidt step for distributed vectors (the coefficient is all-reduced between the steps by the caller):
+//   w -= (*hcoef_dev) v ;  out_dev = vdot(vnext, w) over the local entries (vnext != NULL)  or  sum |w|^2 (vnext == NULL)
+extern "C" int hp_mgs_step(int64_t n, const double* hcoef_dev, const double* v, double* w, const double* vnext, double* out_dev,
+                           void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    HpRedScratch r;
+    if (hp_red_scratch(st, r)) return 2;
+    const unsigned g = hp_red_grid(n);
+    hp_count_launch();
+    if (vnext) hp_axpy_reduce_kernel<0><<<g, HP_RED_THREADS, 0, st>>>(n, (const cplx*)hcoef_dev, (const cplx*)v, (cplx*)w, (const cplx*)vnext,
+                                                                     r.partials, r.ticket, (cplx*)out_dev);
+    else hp_axpy_reduce_kernel<2><<<g, HP_RED_THREADS, 0, st>>>(n, (const cplx*)hcoef_dev, (const cplx*)v, (cplx*)w, (const cplx*)w,
+                                                              r.partials, r.ticket, (cplx*)out_dev);
     HP_CUDA(cudaGetLastError());
     return 0;
 }

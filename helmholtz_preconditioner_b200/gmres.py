@@ -42,6 +42,11 @@ def lartg(f, g):
     return c, fs * g.conjugate() / h, fs * h
 
 
+class CommStats:
+    """how many collective / point-to-point calls the host issued (bench.py reports them per step)"""
+    calls = 0
+
+
 class DeviceVectors:
     """Krylov vector kernels on (a slab of) the field; reductions are summed over `group` if given."""
 
@@ -49,25 +54,44 @@ class DeviceVectors:
         self.lib = _lib.require_device()
         self.nloc, self.device, self.group = nloc, torch.device(device), group
         self.scal = torch.zeros(max(64, restart + 3), dtype=torch.complex128, device=device)
+        self.scalb = None                                    # scalars of a batch of systems, [restart + 3][R]
 
     def reserve(self, restart):
         """hp_mgs writes restart + 2 scalars (coefficients, norm after, norm before)"""
         if self.scal.numel() < restart + 3:
             self.scal = torch.zeros(restart + 3, dtype=torch.complex128, device=self.device)
 
-    def _reduce(self, t):
-        if self.group is not None:
-            import torch.distributed as dist
-            r = torch.view_as_real(t)
-            dist.all_reduce(r, group=self.group)
-        return t
+    def _batch_scal(self, rows, R):
+        if self.scalb is None or self.scalb.shape[0] < rows or self.scalb.shape[1] != R:
+            self.scalb = torch.zeros((max(rows, self.scal.numel()), R), dtype=torch.complex128, device=self.device)
+        return self.scalb
+
+    def _all_reduce(self, t):
+        import torch.distributed as dist
+        CommStats.calls += 1
+        dist.all_reduce(torch.view_as_real(t), group=self.group)
 
     def norm(self, x):
         if self.group is None:
             _lib.check(self.lib.hp_nrm2(self.nloc, _ptr(x), _ptr(self.scal), _stream()), "hp_nrm2")
             return float(self.scal[0].real.item())
         _lib.check(self.lib.hp_dotc(self.nloc, _ptr(x), _ptr(x), _ptr(self.scal), _stream()), "hp_dotc")
-        return math.sqrt(float(self._reduce(self.scal[:1])[0].real.item()))
+        self._all_reduce(self.scal[:1])
+        return math.sqrt(float(self.scal[0].real.item()))
+
+    def norm_batch(self, xs):
+        """norms of several vectors with one all-reduce and one copy to the host"""
+        R = len(xs)
+        sc = self._batch_scal(1, R)[0]
+        for i, x in enumerate(xs):
+            if self.group is None:
+                _lib.check(self.lib.hp_nrm2(self.nloc, _ptr(x), _ptr(sc[i:]), _stream()), "hp_nrm2")
+            else:
+                _lib.check(self.lib.hp_dotc(self.nloc, _ptr(x), _ptr(x), _ptr(sc[i:]), _stream()), "hp_dotc")
+        if self.group is not None:
+            self._all_reduce(sc[:R])
+        v = sc[:R].cpu().numpy().real
+        return [float(t) for t in (v if self.group is None else np.sqrt(v))]
 
     def scale_copy(self, a, x, y):
         a = complex(a)
@@ -79,29 +103,63 @@ class DeviceVectors:
 
     def mgs(self, V, k, w):
         """Modified Gram-Schmidt of w against V[0..k): returns (h[0..k), ||w|| after, ||w|| before)."""
+        return self.mgs_batch([(V, k, w)])[0]
+
+    def mgs_batch(self, items):
+        """The same for several systems that are at the same Arnoldi column k: items = [(V, k, w), ...].  Distributed
+        vectors: the coefficients stay on the device (dot -> all-reduce -> fused axpy + next dot), ONE all-reduce per
+        column for all systems (R x 16 bytes) instead of one per system, and one copy to the host at the end."""
+        R = len(items)
+        k = items[0][1]
+        assert all(it[1] == k for it in items)
         if self.group is None:
-            _lib.check(self.lib.hp_mgs(self.nloc, k, _ptr(V), V.stride(0), _ptr(w), _ptr(self.scal), _stream()), "hp_mgs")
-            h = self.scal[:k + 2].cpu().numpy()
-            return h[:k].copy(), float(h[k].real), float(h[k + 1].real)
-        # distributed: the coefficients stay on the device (dot -> all-reduce -> axpy with a device scalar), one
-        # copy to the host at the end
-        import torch.distributed as dist
-        sc = self.scal
-        _lib.check(self.lib.hp_dotc(self.nloc, _ptr(w), _ptr(w), _ptr(sc[k + 1:]), _stream()), "hp_dotc")
+            if R == 1:
+                V, _, w = items[0]
+                _lib.check(self.lib.hp_mgs(self.nloc, k, _ptr(V), V.stride(0), _ptr(w), _ptr(self.scal), _stream()), "hp_mgs")
+                h = self.scal[:k + 2].cpu().numpy()
+                return [(h[:k].copy(), float(h[k].real), float(h[k + 1].real))]
+            sc = self._batch_scal(k + 2, R)                  # system i uses column i ... stored row-wise per system below
+            flat = sc.view(-1)
+            for i, (V, _, w) in enumerate(items):           # hp_mgs writes k + 2 consecutive scalars per system
+                _lib.check(self.lib.hp_mgs(self.nloc, k, _ptr(V), V.stride(0), _ptr(w), _ptr(flat[i * (k + 2):]), _stream()), "hp_mgs")
+            h = flat[:R * (k + 2)].cpu().numpy().reshape(R, k + 2)
+            return [(h[i, :k].copy(), float(h[i, k].real), float(h[i, k + 1].real)) for i in range(R)]
+        lib, n = self.lib, self.nloc
+        sc = self._batch_scal(k + 2, R)                      # sc[j][i]: coefficient j of system i; rows k, k+1: |w|^2 after, before
+        for i, (V, _, w) in enumerate(items):
+            _lib.check(lib.hp_dotc(n, _ptr(w), _ptr(w), _ptr(sc[k + 1, i:]), _stream()), "hp_dotc")
+            if k > 0:
+                _lib.check(lib.hp_dotc(n, _ptr(V[0]), _ptr(w), _ptr(sc[0, i:]), _stream()), "hp_dotc")
         for j in range(k):
-            _lib.check(self.lib.hp_dotc(self.nloc, _ptr(V[j]), _ptr(w), _ptr(sc[j:]), _stream()), "hp_dotc")
-            dist.all_reduce(torch.view_as_real(sc[j:j + 1]), group=self.group)
-            _lib.check(self.lib.hp_axpy_dev(self.nloc, _ptr(sc[j:]), -1.0, _ptr(V[j]), _ptr(w), _stream()), "hp_axpy_dev")
-        _lib.check(self.lib.hp_dotc(self.nloc, _ptr(w), _ptr(w), _ptr(sc[k:]), _stream()), "hp_dotc")
-        dist.all_reduce(torch.view_as_real(sc[k:k + 2]), group=self.group)
-        h = sc[:k + 2].cpu().numpy()
-        return h[:k].copy(), math.sqrt(float(h[k].real)), math.sqrt(float(h[k + 1].real))
+            self._all_reduce(sc[j, :R])
+            for i, (V, _, w) in enumerate(items):            # w -= h_j v_j and the next local dot in one pass
+                nxt = _ptr(V[j + 1]) if j + 1 < k else 0
+                _lib.check(lib.hp_mgs_step(n, _ptr(sc[j, i:]), _ptr(V[j]), _ptr(w), nxt, _ptr(sc[j + 1, i:]), _stream()), "hp_mgs_step")
+        if k == 0:
+            for i, (V, _, w) in enumerate(items):
+                _lib.check(lib.hp_dotc(n, _ptr(w), _ptr(w), _ptr(sc[0, i:]), _stream()), "hp_dotc")
+        self._all_reduce(sc[k:k + 2, :R].reshape(-1) if sc.shape[1] == R else sc[k:k + 2, :R].contiguous())
+        h = sc[:k + 2, :R].cpu().numpy()
+        return [(h[:k, i].copy(), math.sqrt(float(h[k, i].real)), math.sqrt(float(h[k + 1, i].real))) for i in range(R)]
 
     def combine(self, V, y, x):
         """x += sum_j y[j] V[j]."""
         y = np.ascontiguousarray(np.asarray(y, dtype=np.complex128))
         _lib.check(self.lib.hp_combine(self.nloc, len(y), _ptr(V), V.stride(0), y.ctypes.data, _ptr(x), _stream()),
                    "hp_combine")
+
+
+def _serve(req, matvec, psolve, vec):
+    kind = req[0]
+    if kind == "M":
+        psolve(req[1], req[2])
+    elif kind == "A":
+        matvec(req[1], req[2])
+    elif kind == "norm":
+        return vec.norm(req[1])
+    elif kind == "mgs":
+        return vec.mgs(req[1], req[2], req[3])
+    return None
 
 
 def gmres(matvec, psolve, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None, callback=None, nglobal=None,
@@ -111,52 +169,75 @@ def gmres(matvec, psolve, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=No
     matvec(x, out), psolve(x, out): device operators writing into `out`.  b: device vector (local slab).
     Returns (x, info, hist): hist holds what scipy hands to the legacy callback, one entry per inner iteration.
     """
-    gen = gmres_steps(matvec, b, vec=vec, rtol=rtol, atol=atol, restart=restart, maxiter=maxiter, callback=callback,
+    gen = gmres_steps(b, vec=vec, rtol=rtol, atol=atol, restart=restart, maxiter=maxiter, callback=callback,
                       nglobal=nglobal, health=health)
     try:
         req = next(gen)
         while True:
-            psolve(*req)
-            req = gen.send(None)
+            req = gen.send(_serve(req, matvec, psolve, vec))
     except StopIteration as done:
         return done.value
 
 
-def gmres_batch(matvec, psolve_batch, bs, *, vec, **kw):
-    """The same iteration for several right-hand sides advanced in lock step: every round collects one preconditioner
-    request (x, out) per unfinished system and hands the list to psolve_batch, which may pipeline them (slab.py sends
-    them through the slabs one behind the other).  Returns [(x, info, hist), ...] in the order of `bs`."""
-    gens = [gmres_steps(matvec, b, vec=vec, **kw) for b in bs]
+def gmres_batch(matvec, psolve_batch, bs, *, vec, matvec_batch=None, **kw):
+    """The same iteration for several right-hand sides advanced in lock step.  Every round collects the pending request of
+    each unfinished system and serves them together: preconditioner requests go to psolve_batch as a list (one
+    multi-right-hand-side sweep on one GPU; pipelined through the slabs in slab.py), operator requests to matvec_batch
+    (halo rows of all systems in one exchange), norms and Gram-Schmidt steps to the batched reductions of DeviceVectors
+    (one all-reduce per Arnoldi column for all systems).  Returns [(x, info, hist), ...] in the order of `bs`."""
+    gens = [gmres_steps(b, vec=vec, **kw) for b in bs]
     results = [None] * len(bs)
     reqs = {}
-    for i, g in enumerate(gens):
+
+    def advance(i, value=None, first=False):
         try:
-            reqs[i] = next(g)
+            reqs[i] = next(gens[i]) if first else gens[i].send(value)
         except StopIteration as done:
             results[i] = done.value
+            reqs.pop(i, None)
+
+    for i in range(len(gens)):
+        advance(i, first=True)
     while reqs:
-        order = sorted(reqs)
-        psolve_batch([reqs[i] for i in order])
-        for i in order:
-            try:
-                reqs[i] = gens[i].send(None)
-            except StopIteration as done:
-                results[i] = done.value
-                del reqs[i]
+        by_kind = {}
+        for i in sorted(reqs):
+            key = reqs[i][0] if reqs[i][0] != "mgs" else ("mgs", reqs[i][2])
+            by_kind.setdefault(key, []).append(i)
+        key, idx = next(iter(by_kind.items()))              # lock step: normally a single kind per round
+        kind = key if isinstance(key, str) else key[0]
+        if kind == "M":
+            psolve_batch([(reqs[i][1], reqs[i][2]) for i in idx])
+            vals = [None] * len(idx)
+        elif kind == "A":
+            if matvec_batch is not None:
+                matvec_batch([(reqs[i][1], reqs[i][2]) for i in idx])
+            else:
+                for i in idx:
+                    matvec(reqs[i][1], reqs[i][2])
+            vals = [None] * len(idx)
+        elif kind == "norm":
+            vals = vec.norm_batch([reqs[i][1] for i in idx])
+        else:
+            vals = vec.mgs_batch([(reqs[i][1], reqs[i][2], reqs[i][3]) for i in idx])
+        for i, v in zip(idx, vals):
+            advance(i, v)
     return results
 
 
-def gmres_steps(matvec, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None, callback=None, nglobal=None,
-                health=None):
-    """Generator form of gmres(): yields (x, out) whenever the preconditioner has to be applied (out = M x) and
-    returns (x, info, hist) through StopIteration.  health(): called at every restart boundary (the host is in sync
-    with the device there anyway); raises if a kernel of the operators reported a fault."""
+def gmres_steps(b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None, callback=None, nglobal=None, health=None):
+    """Generator form of gmres().  Yields a request whenever something outside the local vector arithmetic is needed
+    and receives its result through send():
+        ("M", x, out)  out = M x          ("A", x, out)  out = A x
+        ("norm", x) -> ||x||              ("mgs", V, k, w) -> (h[0..k), ||w|| after, ||w|| before)
+    so that a driver can serve the requests of several systems together (gmres_batch).  Returns (x, info, hist)
+    through StopIteration.  health(): called at every restart boundary (the host is in sync with the device there
+    anyway); raises if a kernel of the operators reported a fault."""
     nloc = b.numel()
     n = nglobal if nglobal is not None else nloc
     dev = b.device
     x = torch.zeros_like(b)
     hist = []
-    bnrm2 = vec.norm(b)
+    bnrm2 = yield ("norm", b)
     if bnrm2 == 0:
         return x, 0, hist
     atol = max(float(atol), float(rtol) * bnrm2)
@@ -169,8 +250,8 @@ def gmres_steps(matvec, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None
     r = torch.empty_like(b)
     av = torch.empty_like(b)
     w = torch.empty_like(b)
-    yield (b, w)
-    Mb_nrm2 = vec.norm(w)
+    yield ("M", b, w)
+    Mb_nrm2 = yield ("norm", w)
     ptol_max_factor = 1.0
     ptol = Mb_nrm2 * min(ptol_max_factor, atol / bnrm2)
     presid = 0.0
@@ -183,17 +264,17 @@ def gmres_steps(matvec, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None
             vec.scale_copy(1.0, b, r)
             if bnrm2 < atol:
                 return x, 0, hist
-        yield (r, V[0])
-        tmp = vec.norm(V[0])
+        yield ("M", r, V[0])
+        tmp = yield ("norm", V[0])
         vec.scale_copy(1.0 / tmp, V[0], V[0])
         S = np.zeros(restart + 1, dtype=np.complex128)
         S[0] = tmp
         breakdown = False
         col = 0
         for col in range(restart):
-            matvec(V[col], av)
-            yield (av, w)
-            hcol, h1, h0 = vec.mgs(V, col + 1, w)
+            yield ("A", V[col], av)
+            yield ("M", av, w)
+            hcol, h1, h0 = yield ("mgs", V, col + 1, w)
             hh[col, :col + 1] = hcol
             hh[col, col + 1] = h1
             if h1 <= eps * h0:
@@ -232,10 +313,10 @@ def gmres_steps(matvec, b, *, vec, rtol=1e-5, atol=0.0, restart=20, maxiter=None
         if y[0] != 0:
             y[0] /= hh[0, 0]
         vec.combine(V, y, x)
-        matvec(x, av)
+        yield ("A", x, av)
         vec.scale_copy(-1.0, av, r)
         vec.axpy(1.0, b, r)
-        rnorm = vec.norm(r)
+        rnorm = yield ("norm", r)
         if health is not None:
             health()
         if inner_iter == maxiter:

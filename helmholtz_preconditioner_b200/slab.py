@@ -19,6 +19,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from .gmres import CommStats
+
 os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
 
 
@@ -56,13 +58,28 @@ class SlabSolver:
         self.bufs, self.tfs = [self.buf], []                 # work buffers / parked T_F u_F of a batch of right-hand sides
         self.south = torch.zeros(n, dtype=torch.complex128, device=device)
         self.north = torch.zeros(n, dtype=torch.complex128, device=device)
+        self.halos = []                                      # halo rows of a batch of systems (matvec_batch)
 
     # -- communication helpers ------------------------------------------------------------------------
     def _send(self, t, dst):
+        CommStats.calls += 1
         dist.send(t.contiguous(), dst, group=self.group)
 
     def _recv(self, t, src):
+        CommStats.calls += 1
         dist.recv(t, src, group=self.group)
+
+    def _isend(self, t, dst):
+        CommStats.calls += 1
+        return dist.isend(t, dst, group=self.group)
+
+    def _exchange(self, ops):
+        """one batched non-blocking exchange (a single NCCL group call)"""
+        if not ops:
+            return
+        CommStats.calls += 1
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
 
     def _row(self, j, buf=None):
         """view of global row j inside the ghosted buffer (j0-1 <= j <= j1)."""
@@ -74,18 +91,34 @@ class SlabSolver:
         """out = A x on the slab; exchanges the boundary rows with the neighbours first."""
         n, r, w = self.n, self.rank, self.world
         first, last = x[:n], x[(self.rows - 1) * n:]
-        reqs = []
         if w > 1:
             ops = []
             if r > 0:
                 ops += [dist.P2POp(dist.isend, first.contiguous(), r - 1, self.group), dist.P2POp(dist.irecv, self.south, r - 1, self.group)]
             if r < w - 1:
                 ops += [dist.P2POp(dist.isend, last.contiguous(), r + 1, self.group), dist.P2POp(dist.irecv, self.north, r + 1, self.group)]
-            reqs = dist.batch_isend_irecv(ops) if ops else []
-            for q in reqs:
-                q.wait()
+            self._exchange(ops)
         self.s.matvec_rows(self.j0, self.j1, x, self.south if r > 0 else None, self.north if r < w - 1 else None, out)
         return out
+
+    def matvec_batch(self, pairs):
+        """out_i = A x_i for several systems: the halo rows of all of them travel in one exchange"""
+        n, r, w = self.n, self.rank, self.world
+        R = len(pairs)
+        while len(self.halos) < R:
+            self.halos.append((torch.zeros_like(self.south), torch.zeros_like(self.north)))
+        if w > 1:
+            ops = []
+            for i, (x, _) in enumerate(pairs):
+                so, no = self.halos[i]
+                if r > 0:
+                    ops += [dist.P2POp(dist.isend, x[:n], r - 1, self.group), dist.P2POp(dist.irecv, so, r - 1, self.group)]
+                if r < w - 1:
+                    ops += [dist.P2POp(dist.isend, x[(self.rows - 1) * n:], r + 1, self.group), dist.P2POp(dist.irecv, no, r + 1, self.group)]
+            self._exchange(ops)
+        for i, (x, out) in enumerate(pairs):
+            so, no = self.halos[i]
+            self.s.matvec_rows(self.j0, self.j1, x, so if r > 0 else None, no if r < w - 1 else None, out)
 
     # -- preconditioner -------------------------------------------------------------------------------
     def precond_apply(self, x, out, diag="reference"):
@@ -122,6 +155,10 @@ class SlabSolver:
         return out
 
 
+    def batch_group(self, R):
+        """right-hand sides one sweep launch carries when R are in flight"""
+        return 1
+
     def precond_apply_batch(self, pairs, diag="reference"):
         """out_i = M x_i for every (x_i, out_i) of `pairs`, the right-hand sides sent through the slabs one behind the
         other: while rank r sweeps its strips for right-hand side i, rank r+1 sweeps them for i-1.  Per sweep direction
@@ -146,8 +183,7 @@ class SlabSolver:
                     ops.append(dist.P2POp(dist.isend, owns[i][:n], r - 1, self.group))
                 if r < w - 1:
                     ops.append(dist.P2POp(dist.irecv, self._row(self.j1, self.bufs[i]), r + 1, self.group))
-            for q in dist.batch_isend_irecv(ops):
-                q.wait()
+            self._exchange(ops)
         sends = []
         m_to = min(self.m_hi, n - 1)
         for i in range(R):                                   # forward chain
@@ -161,7 +197,7 @@ class SlabSolver:
             if self.m_lo <= m_to:
                 self.s.sweep_forward_buf(buf, row0, self.m_lo, m_to)
             if r < w - 1:
-                sends.append(dist.isend(self._row(self.j1, buf), r + 1, group=self.group))
+                sends.append(self._isend(self._row(self.j1, buf), r + 1))
         for q in sends:                                      # the rows come back in the backward chain
             q.wait()
         sends = []
@@ -172,7 +208,7 @@ class SlabSolver:
             if self.m_lo <= self.m_hi:
                 self.s.sweep_backward_buf(buf, row0, self.m_hi, self.m_lo, diag)
             if r > 0:
-                sends.append(dist.isend(self._row(self.j0, buf), r - 1, group=self.group))
+                sends.append(self._isend(self._row(self.j0, buf), r - 1))
             else:
                 if R > 1:
                     self.s.front_tf_load(self.tfs[i])
@@ -191,96 +227,3 @@ def distributed_gmres_setup(n, b, omega, const, c_mat, rank, world, group, devic
     m_lo, m_hi = max(b + 1, R[rank] + 1), min(n, R[rank + 1])
     s.setup_preconditioner(P, K, m_lo, m_hi)
     return SlabSolver(s, n, b, rank, world, group, device=device, front_equiv=front_equiv)
-
-
-def bench_distributed(args, w, make_fields, config_dict, ClockSampler):
-    """bench.py for N > 1.  One slab of the grid per rank; Krylov vectors, SpMV halo rows and dot products distributed.
-    mode 'pipelined' (default): the 4096^2 problem, R = 8N right-hand sides (the reference's source, shifted) advance
-    in lock step, their preconditioner applications pipelined through the slabs (precond_apply_batch); value = all
-    GMRES(20) inner iterations of all right-hand sides per second.  mode 'weak': one right-hand side of a problem
-    with 4096^2 points per GPU (the sweeps then run one slab after the other)."""
-    import json
-    import os
-    import time
-    from . import _lib
-    from .gmres import DeviceVectors, gmres, gmres_batch
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    lib = _lib.require_device()
-    omega, c_mat, f_mat = make_fields(w)
-    n, b = w["n"], w["b"]
-    dev = torch.device(f"cuda:{local}")
-    pipelined = args.mp_mode == "pipelined"
-    R = (args.rhs if args.rhs > 0 else 8 * world) if pipelined else 1
-    t0 = time.time()
-    # (the front solves of rank 0 are parallel scans of ~10 us: no re-balancing of the slabs needed, front_equiv = 0)
-    S = distributed_gmres_setup(n, b, omega, w["const"], c_mat, rank, world, None, dev)
-    torch.cuda.synchronize()
-    t_setup = time.time() - t0
-    # right-hand sides: the source of the reference moved along x1 (one shot position per right-hand side)
-    f_hosts = [torch.from_numpy(np.ascontiguousarray(np.roll(f_mat, (i * n) // (2 * R), axis=1)[S.j0:S.j1].ravel())).pin_memory()
-               for i in range(R)]
-    fs = [fh.to(dev) for fh in f_hosts]
-    vec = DeviceVectors(fs[0].numel(), dev, group=dist.group.WORLD)
-    mv = lambda x, out: S.matvec(x, out)                       # noqa: E731
-    psb = lambda reqs: S.precond_apply_batch(reqs)             # noqa: E731
-    ps = lambda x, out: S.precond_apply(x, out)                # noqa: E731
-
-    def iterations(k, rhs):
-        if pipelined:
-            return gmres_batch(mv, psb, rhs, vec=vec, rtol=0.0, atol=0.0, restart=20, maxiter=k, nglobal=n * n)
-        return [gmres(mv, ps, rhs[0], vec=vec, rtol=0.0, atol=0.0, restart=20, maxiter=k, nglobal=n * n)]
-
-    iterations(args.warmup, fs)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    l0 = lib.hp_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); dist.barrier()
-    e0.record()
-    res = iterations(args.steps, fs)
-    e1.record()
-    torch.cuda.synchronize(); dist.barrier()
-    t_dev = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)
-    dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    launches = torch.tensor([lib.hp_launch_count() - l0], device=dev)
-    dist.all_reduce(launches)
-    # end to end: host slabs of every f -> device, K iterations each, slabs of every u -> host
-    u_hosts = [torch.empty(fs[0].numel(), dtype=torch.complex128).pin_memory() for _ in range(R)]
-    torch.cuda.synchronize(); dist.barrier()
-    e0.record()
-    fs2 = [fh.to(dev, non_blocking=True) for fh in f_hosts]
-    res2 = iterations(args.steps, fs2)
-    for uh, (u2, _, _) in zip(u_hosts, res2):
-        uh.copy_(u2, non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize(); dist.barrier()
-    t_e2e = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)
-    dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    fb = torch.tensor([float(S.s.precond_bytes)], device=dev)
-    dist.all_reduce(fb)
-    if rank == 0:
-        clk = clocks.stop()
-        total_steps = args.steps * R
-        cfg = config_dict(w, world)
-        cfg["parallelism"] = (f"slab{world}, {R} right-hand sides pipelined through the slabs" if pipelined
-                              else f"slab{world}, one right-hand side, 4096^2 points per GPU")
-        cfg["rhs_in_flight"] = R
-        out = {"metric": "precond. Krylov iters/s at 4096^2 2D", "value": total_steps / t_dev.item(), "unit": "iters/s",
-               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev.item() / args.steps,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)",
-               "data": "synthetic", "config": cfg,
-               "e2e": {"value": total_steps / t_e2e.item(), "unit": "iters/s",
-                       "h2d_bytes_per_step": R * n * n * 16 / args.steps, "d2h_bytes_per_step": R * (n * n * 16 / args.steps + 16 * 22)},
-               "gpu_launches": int(launches.item()), "clocks": clk,
-               "setup": {"seconds_wall": t_setup, "factor_bytes_all_ranks": fb.item()},
-               "note": ("a step = one GMRES(20) inner iteration of every right-hand side in flight; value counts all of them.  "
-                        "The sweeps of the preconditioner are a sequential chain over the strips, hence over the slabs: one "
-                        "right-hand side keeps one GPU busy at a time, so the right-hand sides follow each other through "
-                        "the slabs (DESIGN.md, multi-GPU); --mp-mode weak runs the single-right-hand-side weak scaling "
-                        "case of BASELINE.json instead"),
-               "residual_last": res[0][2][-1] if res[0][2] else None}
-        print(json.dumps(out))
-    dist.destroy_process_group()

@@ -125,6 +125,13 @@ class HelmholtzSolver:
         self.m_lo, self.m_hi = m_lo, m_hi
         return self
 
+    def set_front(self, front):
+        """switch the front block of a solver that is set up ("blockdiag" | "coupled"); the strips are kept"""
+        self._on_device()
+        _lib.check(self.lib.hp_precond_set_front(self.handle, FRONT_MODES[front], _stream()), "hp_precond_set_front")
+        self.front = front
+        return self
+
     def set_sweep_variant(self, variant):
         """0 = automatic; classic layout: 1 direct, 2 TMA staged, 3 pipelined; cluster layout: 4."""
         _lib.check(self.lib.hp_set_sweep_variant(self.handle, int(variant)), "hp_set_sweep_variant")
@@ -198,6 +205,18 @@ class HelmholtzSolver:
         _lib.check(self.lib.hp_precond_apply(self.handle, _ptr(f), _ptr(out), DIAG_MODES[diag], _stream()),
                    "hp_precond_apply")
         return out
+
+    def batch_group(self, R):
+        """right-hand sides one sweep launch carries when R are in flight"""
+        return 1
+
+    def batch_kernel_name(self, R):
+        return "hp_sweep4_kernel" if self.layout()["colN"] else "hp_sweep2_kernel"
+
+    def precond_apply_batch(self, pairs, diag="reference"):
+        """out_i = M x_i for every (x_i, out_i) of `pairs`"""
+        for x, out in pairs:
+            self.precond_apply(x, out=out, diag=diag)
 
     # staged calls on a slab buffer whose first row is global row `row0` (slab decomposition, slab.py): the
     # kernels index the field by absolute row, so they get the address global row 0 would have

@@ -76,6 +76,8 @@ int hp_set_layout_mode(hp_solver* s, int mode);
  * get_A_FF_block (code.py:178-183: only the b diagonal blocks A_11..A_bb, b independent tridiagonal systems), 1 = the
  * coupled block A[:bn, :bn] of Engquist & Ying's Algorithm 2.3/2.4, i.e. get_Hm(b) (code.py:283-290) solved in full */
 int hp_set_front_mode(hp_solver* s, int mode);
+/* the same switch on a solver that is already set up: factors the front block again with `mode`, keeps the strips */
+int hp_precond_set_front(hp_solver* s, int mode, void* stream);
 /* sweep kernel variant: 0 = automatic; classic layout: 1 = direct loads, 2 = TMA-staged block-synchronous,
  * 3 = pipelined with two hand-overs through L2 per strip; cluster layout: 4 = one hand-over through L2 per strip, the
  * exchanges inside a leaf through distributed shared memory */
@@ -127,6 +129,10 @@ int hp_scale_copy(int64_t n, double a_re, double a_im, const double* x_dev, doub
  *   hcol_dev[2*j..] = vdot(V[j], w); w -= hcol[j] V[j]   sequentially for j = 0..k-1,
  * then hcol_dev[2*k] = ||w|| (after) and hcol_dev[2*k+2] = ||w|| before orthogonalisation (h0). */
 int hp_mgs(int64_t n, int k, const double* V_dev, int64_t ldv, double* w_dev, double* hcol_dev, void* stream);
+/* one fused step of the same recurrence for slab-distributed vectors (the caller all-reduces the coefficient between the
+ * steps): w -= (*hcoef_dev) v, then out_dev = vdot(vnext, w) over the local entries, or sum |w|^2 when vnext is NULL */
+int hp_mgs_step(int64_t n, const double* hcoef_dev, const double* v_dev, double* w_dev, const double* vnext_dev,
+                double* out_dev, void* stream);
 /* x += sum_j y[j] V[j]   (x += y @ v[:col+1, :]); y on the host, 2*k doubles */
 int hp_combine(int64_t n, int k, const double* V_dev, int64_t ldv, const double* y_host, double* x_dev,
                void* stream);

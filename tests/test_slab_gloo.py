@@ -133,3 +133,100 @@ def test_slab_bounds():
     assert slab_bounds(4096, 12, 8) == [512 * r for r in range(9)]
     with pytest.raises(ValueError):
         slab_bounds(40, 12, 8)
+
+
+# ---- the Krylov host logic over gloo: typed requests served in batches, one all-reduce per Arnoldi column ------------
+class NumpyVectors:
+    """DeviceVectors (helmholtz_preconditioner_b200/gmres.py) on CPU tensors: same interface, reductions over gloo."""
+
+    def __init__(self):
+        self.allreduces = 0
+
+    def reserve(self, restart):
+        pass
+
+    def _sum(self, arr):
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=np.complex128)))
+        dist.all_reduce(torch.view_as_real(t))
+        self.allreduces += 1
+        return t.numpy()
+
+    def norm(self, x):
+        return self.norm_batch([x])[0]
+
+    def norm_batch(self, xs):
+        v = self._sum([np.vdot(x.numpy(), x.numpy()) for x in xs])
+        return [float(np.sqrt(t.real)) for t in v]
+
+    def scale_copy(self, a, x, y):
+        y.copy_(torch.from_numpy(a * x.numpy()))
+
+    def axpy(self, a, x, y):
+        y.numpy()[:] += a * x.numpy()
+
+    def mgs(self, V, k, w):
+        return self.mgs_batch([(V, k, w)])[0]
+
+    def mgs_batch(self, items):
+        R, k = len(items), items[0][1]
+        h0 = self._sum([np.vdot(w.numpy(), w.numpy()) for _, _, w in items])
+        H = np.zeros((k, R), complex)
+        for j in range(k):
+            d = self._sum([np.vdot(V[j].numpy(), w.numpy()) for V, _, w in items])
+            H[j] = d
+            for i, (V, _, w) in enumerate(items):
+                w.numpy()[:] -= d[i] * V[j].numpy()
+        h1 = self._sum([np.vdot(w.numpy(), w.numpy()) for _, _, w in items])
+        return [(H[:, i].copy(), float(np.sqrt(h1[i].real)), float(np.sqrt(h0[i].real))) for i in range(R)]
+
+    def combine(self, V, y, x):
+        x.numpy()[:] += np.asarray(y) @ V[:len(y)].numpy()
+
+
+def _gmres_worker(rank, world, port, n, b, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from helmholtz_preconditioner_b200.slab import SlabSolver
+    from helmholtz_preconditioner_b200.gmres import gmres, gmres_batch
+    omega = 2 * np.pi * 4 + 2j
+    c_mat, f_mat = orc.init_c1_f1(omega, n)
+    be = NumpyBackend(n, b, omega, 61.0, c_mat)
+    S = SlabSolver(be, n, b, rank, world)
+    fs = [f_mat, np.roll(f_mat, 7, axis=1), np.roll(f_mat, -5, axis=1)]
+    loc = [torch.from_numpy(np.ascontiguousarray(f[S.j0:S.j1].ravel().astype(np.complex128))) for f in fs]
+    vec = NumpyVectors()
+    kw = dict(vec=vec, rtol=1e-3, restart=20, maxiter=12, nglobal=n * n)
+    batch = gmres_batch(lambda x, o: S.matvec(x, o), lambda reqs: S.precond_apply_batch(reqs), loc,
+                        matvec_batch=lambda reqs: S.matvec_batch(reqs), **kw)
+    n_batch = vec.allreduces
+    vec.allreduces = 0
+    one = [gmres(lambda x, o: S.matvec(x, o), lambda x, o: S.precond_apply(x, o), f, **kw) for f in loc]
+    n_one = vec.allreduces
+    ret[rank] = dict(j0=S.j0, j1=S.j1, batch=[(u.numpy().copy(), info, hist) for u, info, hist in batch],
+                     one=[(u.numpy().copy(), info, hist) for u, info, hist in one], n_batch=n_batch, n_one=n_one)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_distributed_gmres_batch_matches_oracle(world):
+    """gmres_batch over slabs (gloo): every right-hand side follows the oracle's scipy-restated GMRES, the batched
+    drivers give what the one-by-one driver gives, with 1/R of the all-reduces."""
+    n, b = 40, 5
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gmres_worker, args=(world, _free_port(), n, b, ret), nprocs=world, join=True)
+    omega = 2 * np.pi * 4 + 2j
+    c_mat, f_mat = orc.init_c1_f1(omega, n)
+    h = 1 / (n + 1)
+    A = orc.build_A_matrix(b, 61.0, b * h, omega, h, n, c_mat)
+    P = orc.SweepingPreconditioner(b, 61.0, b * h, omega, h, n, c_mat)          # reference diagonal, as the stand-in
+    fs = [f_mat, np.roll(f_mat, 7, axis=1), np.roll(f_mat, -5, axis=1)]
+    for i, f in enumerate(fs):
+        u0, info0, hist0 = orc.gmres_scipy_restated(lambda x: A @ x, P.apply, f.ravel().astype(np.complex128), rtol=1e-3, maxiter=12)
+        for kind in ("batch", "one"):
+            u = np.concatenate([ret[r][kind][i][0] for r in range(world)])
+            info, hist = ret[0][kind][i][1], ret[0][kind][i][2]
+            assert info == info0 and len(hist) == len(hist0)
+            assert np.allclose(hist, hist0, rtol=1e-8)
+            assert np.linalg.norm(u - u0) / np.linalg.norm(u0) < 1e-8
+    assert ret[0]["n_batch"] * 3 == ret[0]["n_one"]
