@@ -43,6 +43,10 @@ SIGNATURES = {
     "hp_sweep_backward": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "hp_front_end": (_i, [_vp, _vp, _vp]),
     "hp_precond_apply": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "hp_multi_max": (_i, [_vp]),
+    "hp_sweep_forward_multi": (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _vp]),
+    "hp_sweep_backward_multi": (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _i, _vp]),
+    "hp_precond_apply_multi": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), _i, _vp]),
     "hp_strip_apply": (_i, [_vp, _i, _vp, _vp, _vp]),
     "hp_strip_layout": (_i, [_vp, _ip, _ip, _ip, _ip, _ip, _ip, C.POINTER(_i64), _ip, _ip, _ip]),
     "hp_strip_packets": (_i, [_vp, _i, _vp]),

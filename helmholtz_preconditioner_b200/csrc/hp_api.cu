@@ -110,7 +110,7 @@ extern "C" int hp_destroy(hp_solver* s) {
     hp_free_strips(s);
     cudaFree(s->s1t); cudaFree(s->is1t); cudaFree(s->s2t); cudaFree(s->is2t);
     cudaFree(s->c_mat); cudaFree(s->kappa); cudaFree(s->status);
-    cudaFree(s->f_low); cudaFree(s->f_invd); cudaFree(s->f_up); cudaFree(s->TF);
+    cudaFree(s->f_low); cudaFree(s->f_invd); cudaFree(s->f_up); cudaFree(s->TF); cudaFree(s->TFm);
     hp_front_coupled_free(s);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     delete s;
@@ -206,6 +206,42 @@ extern "C" int hp_precond_apply(hp_solver* s, const double* f_dev, double* u_dev
         if ((rc = hp_sweep_backward(s, u_dev, n, b + 1, diag_mode, stream))) return rc;
     }
     return hp_front_end(s, u_dev, stream);
+}
+
+// algo2_4 for R right-hand sides with ONE pass over the strip generators per sweep direction (csrc/hp_sweep4m.cu).
+// R must be 1, 2, 4 or 8 and at most hp_multi_max(s).
+extern "C" int hp_precond_apply_multi(hp_solver* s, int R, const double* const* f_devs, double* const* u_devs, int diag_mode,
+                                      void* stream) {
+    if (!s || !f_devs || !u_devs) { hp_set_error("hp_precond_apply_multi: null argument"); return 1; }
+    if (s->m_lo != s->b + 1 || s->m_hi != s->n) {
+        hp_set_error("hp_precond_apply_multi: solver holds strips %d..%d, needs %d..%d (use the staged calls for slabs)",
+                     s->m_lo, s->m_hi, s->b + 1, s->n);
+        return 1;
+    }
+    if (R < 1 || R > hp_multi_max(s) || (R & (R - 1))) {
+        hp_set_error("hp_precond_apply_multi: R must be a power of two <= %d, got %d", hp_multi_max(s), R);
+        return 1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = s->n, b = s->b;
+    const size_t tf = (size_t)b * n;
+    if (!s->TFm) HP_CUDA(cudaMalloc(&s->TFm, sizeof(cplx) * tf * 8));
+    int rc;
+    for (int r = 0; r < R; ++r) {
+        if (f_devs[r] != u_devs[r])
+            HP_CUDA(cudaMemcpyAsync(u_devs[r], f_devs[r], sizeof(cplx) * (size_t)n * n, cudaMemcpyDeviceToDevice, st));
+        if ((rc = hp_front_begin(s, u_devs[r], stream))) return rc;
+        HP_CUDA(cudaMemcpyAsync(s->TFm + r * tf, s->TF, sizeof(cplx) * tf, cudaMemcpyDeviceToDevice, st));
+    }
+    if (b < n) {
+        if ((rc = hp_sweep_forward_multi(s, R, u_devs, b + 1, n - 1, stream))) return rc;
+        if ((rc = hp_sweep_backward_multi(s, R, u_devs, n, b + 1, diag_mode, stream))) return rc;
+    }
+    for (int r = 0; r < R; ++r) {
+        HP_CUDA(cudaMemcpyAsync(s->TF, s->TFm + r * tf, sizeof(cplx) * tf, cudaMemcpyDeviceToDevice, st));
+        if ((rc = hp_front_end(s, u_devs[r], stream))) return rc;
+    }
+    return 0;
 }
 
 extern "C" int hp_strip_layout(hp_solver* s, int* P, int* K, int* QP, int* CW, int* NS, int* NR, int64_t* PK,

@@ -80,6 +80,8 @@ struct hp_solver {
     long long* dbg = nullptr;     // optional per-phase cycle counters of the sweep kernel [G][8]
     int sweep_variant = 0;        // 0 = automatic; classic layout: 1 direct, 2 TMA staged, 3 pipelined; cluster layout: 4
     int layout_mode = 0;          // 0 = automatic (cluster layout when a partition exists), 1 = classic, 2 = cluster
+    int multi_ok[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // multi-vector kernel with RT right-hand sides: 0 unknown, 1 fits, -1 does not
+    cplx* TFm = nullptr;          // [HP_RMAX][b][n] parked T_F u_F of the right-hand sides of a multi-vector application
     unsigned int* bar = nullptr;
     int* status = nullptr;        // device flag: non-zero when a pivot vanished during setup
     // optional CUDA-event timing of the sweep launches (hp_profile_enable / hp_profile_read)
@@ -112,3 +114,5 @@ int hp_front_coupled_solve(hp_solver* s, int rhs_mode, int out_mode, const cplx*
 // hp_sweep.cu : mode 0 = forward, 1 = backward, 2 = single strip apply (vin -> yout)
 int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout, int m_from, int m_to,
                     int diag_mode, cudaStream_t st);
+// the same sweep for R right-hand sides in one launch (cluster layout, csrc/hp_sweep4m.cu): mode 0 forward, 1 backward
+int hp_sweep_launch_multi(hp_solver* s, int mode, int R, cplx* const* um, int m_from, int m_to, int diag_mode, cudaStream_t st);

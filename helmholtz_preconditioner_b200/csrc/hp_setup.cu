@@ -1215,6 +1215,7 @@ void hp_free_strips(hp_solver* s) {
     cudaFree(s->xch); s->xch = nullptr;
     cudaFree(s->bar); s->bar = nullptr;
     s->m_lo = 0; s->m_hi = -1; s->bytes = 0;
+    for (int i = 0; i < 9; ++i) s->multi_ok[i] = 0;
 }
 
 // developer trace (HP_SETUP_TRACE=1): wall-clock milliseconds since the start of hp_setup_strips at the named points
@@ -1265,7 +1266,7 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     HP_CUDA(cudaMemsetAsync(s->packets, 0, pbytes, st));
     tr.mark("packets cleared", st, true);
     size_t xch_classic = (size_t)n + (size_t)L.G * 2 * b + (size_t)L.P * 2 * b + L.NSP + L.P;
-    size_t xch_cluster = (size_t)L.G * b + (size_t)std::max(L.NS, 1) * (L.P | 1);
+    size_t xch_cluster = ((size_t)L.G * b + (size_t)std::max(L.NS, 1) * (L.P | 1)) * 8;   // x HP_RMAX right-hand sides per launch
     HP_CUDA(cudaMalloc(&s->xch, sizeof(cplx) * 4 * std::max(xch_classic, xch_cluster)));
     HP_CUDA(cudaMalloc(&s->bar, sizeof(unsigned int) * (4 + L.P)));
     HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int) * (4 + L.P), st));

@@ -426,6 +426,39 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
     return 0;
 }
 
+int hp_sweep_launch_multi(hp_solver* s, int mode, int R, cplx* const* um, int m_from, int m_to, int diag_mode, cudaStream_t st) {
+    if (!s->packets) { hp_set_error("sweep: preconditioner not set up"); return 1; }
+    if (R < 1 || R > HP_RMAX || hp_sweep4m_supported(s, R)) { hp_set_error("sweep: %d right-hand sides per launch not supported by this layout", R); return 1; }
+    int lo = mode == 1 ? m_to : m_from, hi = mode == 1 ? m_from : m_to;
+    if (lo > hi) return 0;
+    if (lo < s->m_lo || hi > s->m_hi) {
+        hp_set_error("sweep: strips %d..%d requested, solver holds %d..%d", lo, hi, s->m_lo, s->m_hi);
+        return 1;
+    }
+    const HpLayout& L = s->lay;
+    HpSweepArgs a;
+    a.n = s->n; a.b = s->b; a.lay = s->lay;
+    a.leaf_start = s->leaf_start; a.leaf_q = s->leaf_q; a.sep = s->sep;
+    a.packets = s->packets; a.mleaf = s->mleaf; a.rsep = s->rsep; a.m_lo = s->m_lo;
+    a.mode = mode; a.m_from = m_from; a.m_to = m_to; a.diag_mode = diag_mode;
+    a.u = um[0]; a.vin = nullptr; a.yout = nullptr;
+    for (int r = 0; r < HP_RMAX; ++r) a.um[r] = r < R ? um[r] : nullptr;
+    a.xch = s->xch; a.bar = s->bar;
+    a.oGP = 0; a.oXS = (size_t)L.G * s->b * R; a.oGR = a.oVS = 0;
+    a.slot_stride = a.oXS + (size_t)std::max(L.NS, 1) * (L.P | 1) * R;
+    a.s2t = s->s2t; a.is1t = s->is1t;
+    a.ih2 = 1.0 / (s->pml.h * s->pml.h);
+    a.dbg = s->dbg;
+    HP_CUDA(cudaMemsetAsync(s->xch, 0xFF, sizeof(cplx) * HP_RING * a.slot_stride, st));
+    HP_CUDA(cudaMemsetAsync(s->bar + 1, 0, sizeof(unsigned int), st));
+    hp_count_launch();
+    hp_profile_begin(s, st);
+    if (hp_sweep4m_launch(s, a, R, st)) return 2;
+    hp_profile_end(s, st, (int64_t)(hi - lo + 1) * ((int64_t)L.G * L.PK + 3 * (int64_t)s->n * R + (int64_t)(L.P - 1) * 3 * s->b * s->b) *
+                              (int64_t)sizeof(cplx));
+    return 0;
+}
+
 // 0 = fine; 1 = a CTA of a sweep kernel gave up waiting for exchange data (synchronises the device)
 extern "C" int hp_sweep_status(hp_solver* s) {
     if (!s || !s->bar) return 0;
@@ -443,6 +476,22 @@ extern "C" int hp_sweep_forward(hp_solver* s, double* u_dev, int m_from, int m_t
 extern "C" int hp_sweep_backward(hp_solver* s, double* u_dev, int m_from, int m_to, int diag_mode, void* stream) {
     if (!s) { hp_set_error("hp_sweep_backward: null solver"); return 1; }
     return hp_sweep_launch(s, 1, (cplx*)u_dev, nullptr, nullptr, m_from, m_to, diag_mode, (cudaStream_t)stream);
+}
+
+// largest number of right-hand sides one sweep launch can carry with the layout of this solver (1, 2, 4 or 8)
+extern "C" int hp_multi_max(hp_solver* s) {
+    if (!s || !s->packets) return 1;
+    for (int R = HP_RMAX; R > 1; R >>= 1)
+        if (!hp_sweep4m_supported(s, R)) return R;
+    return 1;
+}
+extern "C" int hp_sweep_forward_multi(hp_solver* s, int R, double* const* u_devs, int m_from, int m_to, void* stream) {
+    if (!s || !u_devs) { hp_set_error("hp_sweep_forward_multi: null argument"); return 1; }
+    return hp_sweep_launch_multi(s, 0, R, (cplx* const*)u_devs, m_from, m_to, 0, (cudaStream_t)stream);
+}
+extern "C" int hp_sweep_backward_multi(hp_solver* s, int R, double* const* u_devs, int m_from, int m_to, int diag_mode, void* stream) {
+    if (!s || !u_devs) { hp_set_error("hp_sweep_backward_multi: null argument"); return 1; }
+    return hp_sweep_launch_multi(s, 1, R, (cplx* const*)u_devs, m_from, m_to, diag_mode, (cudaStream_t)stream);
 }
 
 extern "C" int hp_strip_apply(hp_solver* s, int m, const double* v_dev, double* y_dev, void* stream) {

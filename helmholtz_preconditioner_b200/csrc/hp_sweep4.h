@@ -13,6 +13,10 @@ struct Hp4Plan {
 };
 
 struct HpSweepArgs;
-int hp_sweep4_plan(const HpLayout& L, int b, size_t max_smem, Hp4Plan& pl);
+int hp_sweep4_plan(const HpLayout& L, int b, size_t max_smem, Hp4Plan& pl, int RT = 1);   // RT right-hand sides per launch
 int hp_sweep4_max_clusters(const HpLayout& L, int b);
 int hp_sweep4_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st);
+bool hp_profiler_attached();
+// csrc/hp_sweep4m.cu: RT right-hand sides per launch
+int hp_sweep4m_supported(hp_solver* s, int RT);      // 0 = this layout can run RT right-hand sides per launch
+int hp_sweep4m_launch(hp_solver* s, HpSweepArgs& a, int RT, cudaStream_t st);

@@ -3,6 +3,7 @@
 #include "hp_internal.cuh"
 
 #define HP_RING 4
+#define HP_RMAX 8           // right-hand sides one launch of the multi-vector cluster kernel carries at most
 #define HP_SPIN_LIMIT (1u << 21)
 
 struct HpSweepArgs {
@@ -15,6 +16,7 @@ struct HpSweepArgs {
     int m_lo;
     int mode, m_from, m_to, diag_mode;
     cplx* u;
+    cplx* um[HP_RMAX];        // multi-vector cluster kernel (csrc/hp_sweep4m.cu): the fields of the right-hand sides
     const cplx* vin;
     cplx* yout;
     cplx* xch;                // exchange ring: HP_RING slots of slot_stride complex numbers

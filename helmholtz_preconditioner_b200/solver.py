@@ -70,6 +70,7 @@ class HelmholtzSolver:
                                           cptr, on_dev, _stream()), "hp_create")
         self.handle = h
         self.m_lo, self.m_hi = 0, -1
+        self.max_group = 8            # cap on the right-hand sides per sweep launch (1 = one launch per vector)
 
     def close(self):
         if getattr(self, "handle", None):
@@ -206,17 +207,53 @@ class HelmholtzSolver:
                    "hp_precond_apply")
         return out
 
+    @property
+    def multi_max(self):
+        """right-hand sides one sweep launch can carry with the partition in use (1, 2, 4 or 8)"""
+        return int(self.lib.hp_multi_max(self.handle))
+
     def batch_group(self, R):
         """right-hand sides one sweep launch carries when R are in flight"""
-        return 1
+        g = 1
+        while g * 2 <= min(R, self.multi_max, self.max_group):
+            g *= 2
+        return g
 
     def batch_kernel_name(self, R):
+        if self.batch_group(R) > 1:
+            return "hp_sweep4m_kernel"
         return "hp_sweep4_kernel" if self.layout()["colN"] else "hp_sweep2_kernel"
 
+    @staticmethod
+    def _ptr_array(ts):
+        return (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+    def precond_apply_multi(self, fs, outs, diag="reference"):
+        """algo2_4 on R = len(fs) vectors with one pass over the strip generators per sweep (R in {1, 2, 4, 8})."""
+        self._on_device()
+        _lib.check(self.lib.hp_precond_apply_multi(self.handle, len(fs), self._ptr_array(fs), self._ptr_array(outs), DIAG_MODES[diag],
+                                                   _stream()), "hp_precond_apply_multi")
+        return outs
+
     def precond_apply_batch(self, pairs, diag="reference"):
-        """out_i = M x_i for every (x_i, out_i) of `pairs`"""
-        for x, out in pairs:
-            self.precond_apply(x, out=out, diag=diag)
+        """out_i = M x_i for every (x_i, out_i) of `pairs`, in groups of batch_group() right-hand sides per launch"""
+        i = 0
+        while i < len(pairs):
+            g = self.batch_group(len(pairs) - i)
+            if g == 1:
+                self.precond_apply(pairs[i][0], out=pairs[i][1], diag=diag)
+            else:
+                self.precond_apply_multi([p[0] for p in pairs[i:i + g]], [p[1] for p in pairs[i:i + g]], diag=diag)
+            i += g
+
+    def sweep_forward_multi_buf(self, bufs, row0, m_from, m_to):
+        arr = (C.c_void_p * len(bufs))(*[self._base(t, row0) for t in bufs])
+        _lib.check(self.lib.hp_sweep_forward_multi(self.handle, len(bufs), arr, m_from, m_to, _stream()), "hp_sweep_forward_multi")
+
+    def sweep_backward_multi_buf(self, bufs, row0, m_from, m_to, diag="reference"):
+        arr = (C.c_void_p * len(bufs))(*[self._base(t, row0) for t in bufs])
+        _lib.check(self.lib.hp_sweep_backward_multi(self.handle, len(bufs), arr, m_from, m_to, DIAG_MODES[diag], _stream()),
+                   "hp_sweep_backward_multi")
 
     # staged calls on a slab buffer whose first row is global row `row0` (slab decomposition, slab.py): the
     # kernels index the field by absolute row, so they get the address global row 0 would have

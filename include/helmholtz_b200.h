@@ -102,6 +102,14 @@ int hp_front_end(hp_solver* s, double* u_dev, void* stream);
  * sides are in flight: dir 0 copies solver -> buf_dev, dir 1 copies buf_dev -> solver */
 int hp_front_tf_copy(hp_solver* s, double* buf_dev, int dir, void* stream);
 int hp_precond_apply(hp_solver* s, const double* f_dev, double* u_dev, int diag_mode, void* stream);
+/* Several right-hand sides per pass over the strip generators (algo2_4 applied to R vectors; the reference applies it to
+ * one vector per call, code.py:510-511).  u_devs / f_devs: HOST arrays of R device pointers (n*n complex each); R must be
+ * 1, 2, 4 or 8 and <= hp_multi_max(s) (1 when the partition of the strips does not fit the multi-vector kernel).  Per
+ * right-hand side the result equals hp_sweep_forward / hp_sweep_backward / hp_precond_apply up to rounding. */
+int hp_multi_max(hp_solver* s);
+int hp_sweep_forward_multi(hp_solver* s, int R, double* const* u_devs, int m_from, int m_to, void* stream);
+int hp_sweep_backward_multi(hp_solver* s, int R, double* const* u_devs, int m_from, int m_to, int diag_mode, void* stream);
+int hp_precond_apply_multi(hp_solver* s, int R, const double* const* f_devs, double* const* u_devs, int diag_mode, void* stream);
 /* y = T_m v : last n entries of H_m^{-1} [0; v]  (lu_Hm_ra[m-b-1].solve(u_temp)[-n:], code.py:370) */
 int hp_strip_apply(hp_solver* s, int m, const double* v_dev, double* y_dev, void* stream);
 /* test hooks: the partition in use, and a host copy of one strip's packed generators
