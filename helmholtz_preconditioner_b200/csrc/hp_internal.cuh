@@ -81,6 +81,7 @@ struct hp_solver {
     int sweep_variant = 0;        // 0 = automatic; classic layout: 1 direct, 2 TMA staged, 3 pipelined; cluster layout: 4
     int layout_mode = 0;          // 0 = automatic (cluster layout when a partition exists), 1 = classic, 2 = cluster
     int multi_ok[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // multi-vector kernel with RT right-hand sides: 0 unknown, 1 fits, -1 does not
+    int dmma_ok = 0;              // tensor-core kernel (8 right-hand sides): 0 unknown, 1 fits, -1 does not
     cplx* TFm = nullptr;          // [HP_RMAX][b][n] parked T_F u_F of the right-hand sides of a multi-vector application
     unsigned int* bar = nullptr;
     int* status = nullptr;        // device flag: non-zero when a pivot vanished during setup

@@ -1216,6 +1216,7 @@ void hp_free_strips(hp_solver* s) {
     cudaFree(s->bar); s->bar = nullptr;
     s->m_lo = 0; s->m_hi = -1; s->bytes = 0;
     for (int i = 0; i < 9; ++i) s->multi_ok[i] = 0;
+    s->dmma_ok = 0;
 }
 
 // developer trace (HP_SETUP_TRACE=1): wall-clock milliseconds since the start of hp_setup_strips at the named points

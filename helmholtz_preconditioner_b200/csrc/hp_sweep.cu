@@ -428,7 +428,8 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
 
 int hp_sweep_launch_multi(hp_solver* s, int mode, int R, cplx* const* um, int m_from, int m_to, int diag_mode, cudaStream_t st) {
     if (!s->packets) { hp_set_error("sweep: preconditioner not set up"); return 1; }
-    if (R < 1 || R > HP_RMAX || hp_sweep4m_supported(s, R)) { hp_set_error("sweep: %d right-hand sides per launch not supported by this layout", R); return 1; }
+    const bool tensor = R == 8 && !hp_sweep4d_supported(s);
+    if (R < 1 || R > HP_RMAX || (!tensor && hp_sweep4m_supported(s, R))) { hp_set_error("sweep: %d right-hand sides per launch not supported by this layout", R); return 1; }
     int lo = mode == 1 ? m_to : m_from, hi = mode == 1 ? m_from : m_to;
     if (lo > hi) return 0;
     if (lo < s->m_lo || hi > s->m_hi) {
@@ -453,7 +454,7 @@ int hp_sweep_launch_multi(hp_solver* s, int mode, int R, cplx* const* um, int m_
     HP_CUDA(cudaMemsetAsync(s->bar + 1, 0, sizeof(unsigned int), st));
     hp_count_launch();
     hp_profile_begin(s, st);
-    if (hp_sweep4m_launch(s, a, R, st)) return 2;
+    if (tensor ? hp_sweep4d_launch(s, a, st) : hp_sweep4m_launch(s, a, R, st)) return 2;
     hp_profile_end(s, st, (int64_t)(hi - lo + 1) * ((int64_t)L.G * L.PK + 3 * (int64_t)s->n * R + (int64_t)(L.P - 1) * 3 * s->b * s->b) *
                               (int64_t)sizeof(cplx));
     return 0;
@@ -481,6 +482,7 @@ extern "C" int hp_sweep_backward(hp_solver* s, double* u_dev, int m_from, int m_
 // largest number of right-hand sides one sweep launch can carry with the layout of this solver (1, 2, 4 or 8)
 extern "C" int hp_multi_max(hp_solver* s) {
     if (!s || !s->packets) return 1;
+    if (!hp_sweep4d_supported(s)) return 8;
     for (int R = HP_RMAX; R > 1; R >>= 1)
         if (!hp_sweep4m_supported(s, R)) return R;
     return 1;

@@ -20,3 +20,6 @@ bool hp_profiler_attached();
 // csrc/hp_sweep4m.cu: RT right-hand sides per launch
 int hp_sweep4m_supported(hp_solver* s, int RT);      // 0 = this layout can run RT right-hand sides per launch
 int hp_sweep4m_launch(hp_solver* s, HpSweepArgs& a, int RT, cudaStream_t st);
+// csrc/hp_sweep4d.cu: 8 right-hand sides per launch on the FP64 tensor cores
+int hp_sweep4d_supported(hp_solver* s);
+int hp_sweep4d_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st);

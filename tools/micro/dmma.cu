@@ -39,3 +39,4 @@ int main() {
     }
     return 0;
 }
+// second experiment (dmma mix): do DMMA and DFMA share one datapath?  Half of the warps of every SM issue DMMA, the other half DFMA.
