@@ -156,14 +156,15 @@ class SlabSolver:
 
 
     def batch_group(self, R):
-        """right-hand sides one sweep launch carries when R are in flight"""
-        return 1
+        """right-hand sides one sweep launch carries when R are in flight (the multi-vector kernels of the backend)"""
+        return self.s.batch_group(R) if hasattr(self.s, "batch_group") else 1
 
     def precond_apply_batch(self, pairs, diag="reference"):
-        """out_i = M x_i for every (x_i, out_i) of `pairs`, the right-hand sides sent through the slabs one behind the
-        other: while rank r sweeps its strips for right-hand side i, rank r+1 sweeps them for i-1.  Per sweep direction
-        a batch of R takes (world - 1 + R) slab sweeps instead of R * world, the rows handed over are posted as
-        non-blocking sends so that a rank goes on with the next right-hand side at once."""
+        """out_i = M x_i for every (x_i, out_i) of `pairs`.  The right-hand sides travel through the slabs in groups: a group
+        is swept by ONE launch of the multi-vector kernel per slab (the strip generators are streamed once for the whole
+        group), and the groups follow each other through the slabs: while rank r sweeps its strips for group j, rank
+        r+1 sweeps them for group j-1.  Per sweep direction G groups take (world - 1 + G) slab sweeps instead of G * world;
+        the rows handed over are posted as non-blocking sends so that a rank goes on with the next group at once."""
         n, b, r, w = self.n, self.b, self.rank, self.world
         R = len(pairs)
         while len(self.bufs) < R:
@@ -175,7 +176,7 @@ class SlabSolver:
         owns = [self.bufs[i][n:(self.rows + 1) * n] for i in range(R)]
         for i, (x, _) in enumerate(pairs):
             owns[i].copy_(x)
-        # ghost rows above (initial values of the first row of the next slab), all right-hand sides in one batch
+        # ghost rows above (initial values of the first row of the next slab), all right-hand sides in one exchange
         if w > 1:
             ops = []
             for i in range(R):
@@ -184,35 +185,53 @@ class SlabSolver:
                 if r < w - 1:
                     ops.append(dist.P2POp(dist.irecv, self._row(self.j1, self.bufs[i]), r + 1, self.group))
             self._exchange(ops)
+        groups, i = [], 0
+        while i < R:
+            g = self.batch_group(R - i)
+            groups.append(list(range(i, i + g)))
+            i += g
+        multi = hasattr(self.s, "sweep_forward_multi_buf")
         sends = []
         m_to = min(self.m_hi, n - 1)
-        for i in range(R):                                   # forward chain
-            buf = self.bufs[i]
-            if r == 0:
-                self.s.front_begin_buf(buf, row0)
-                if R > 1:
-                    self.s.front_tf_save(self.tfs[i])
-            else:
-                self._recv(self._row(self.j0, buf), r - 1)
+        for grp in groups:                                   # forward chain
+            bufs = [self.bufs[i] for i in grp]
+            for i in grp:
+                if r == 0:
+                    self.s.front_begin_buf(self.bufs[i], row0)
+                    if R > 1:
+                        self.s.front_tf_save(self.tfs[i])
+            if r > 0:
+                self._exchange([dist.P2POp(dist.irecv, self._row(self.j0, bf), r - 1, self.group) for bf in bufs])
             if self.m_lo <= m_to:
-                self.s.sweep_forward_buf(buf, row0, self.m_lo, m_to)
+                if multi and len(grp) > 1:
+                    self.s.sweep_forward_multi_buf(bufs, row0, self.m_lo, m_to)
+                else:
+                    for bf in bufs:
+                        self.s.sweep_forward_buf(bf, row0, self.m_lo, m_to)
             if r < w - 1:
-                sends.append(self._isend(self._row(self.j1, buf), r + 1))
+                CommStats.calls += 1
+                sends += dist.batch_isend_irecv([dist.P2POp(dist.isend, self._row(self.j1, bf), r + 1, self.group) for bf in bufs])
         for q in sends:                                      # the rows come back in the backward chain
             q.wait()
         sends = []
-        for i in range(R):                                   # backward chain
-            buf = self.bufs[i]
+        for grp in groups:                                   # backward chain
+            bufs = [self.bufs[i] for i in grp]
             if r < w - 1:
-                self._recv(self._row(self.j1, buf), r + 1)
+                self._exchange([dist.P2POp(dist.irecv, self._row(self.j1, bf), r + 1, self.group) for bf in bufs])
             if self.m_lo <= self.m_hi:
-                self.s.sweep_backward_buf(buf, row0, self.m_hi, self.m_lo, diag)
+                if multi and len(grp) > 1:
+                    self.s.sweep_backward_multi_buf(bufs, row0, self.m_hi, self.m_lo, diag)
+                else:
+                    for bf in bufs:
+                        self.s.sweep_backward_buf(bf, row0, self.m_hi, self.m_lo, diag)
             if r > 0:
-                sends.append(self._isend(self._row(self.j0, buf), r - 1))
+                CommStats.calls += 1
+                sends += dist.batch_isend_irecv([dist.P2POp(dist.isend, self._row(self.j0, bf), r - 1, self.group) for bf in bufs])
             else:
-                if R > 1:
-                    self.s.front_tf_load(self.tfs[i])
-                self.s.front_end_buf(buf, row0)
+                for i in grp:
+                    if R > 1:
+                        self.s.front_tf_load(self.tfs[i])
+                    self.s.front_end_buf(self.bufs[i], row0)
         for q in sends:
             q.wait()
         for i, (_, out) in enumerate(pairs):

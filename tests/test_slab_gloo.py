@@ -62,6 +62,23 @@ class NumpyBackend:
                 v += self.P.up[m - 1] * u[m - r0]
             u[m - 1 - r0] = u[m - 1 - r0] - self.P.T(m, v)
 
+    # multi-vector entry points of the device backend: here one vector after the other (the schedule is what is tested)
+    group = 2
+
+    def batch_group(self, R):
+        g = 1
+        while g * 2 <= min(R, self.group):
+            g *= 2
+        return g
+
+    def sweep_forward_multi_buf(self, bufs, row0, m_from, m_to):
+        for bf in bufs:
+            self.sweep_forward_buf(bf, row0, m_from, m_to)
+
+    def sweep_backward_multi_buf(self, bufs, row0, m_from, m_to, diag):
+        for bf in bufs:
+            self.sweep_backward_buf(bf, row0, m_from, m_to, diag)
+
     def matvec_rows(self, j_lo, j_hi, x, south, north, out):
         n = self.n
         c1, c2, c3, c4, c5 = (c[j_lo:j_hi] for c in self.c)
