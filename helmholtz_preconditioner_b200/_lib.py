@@ -24,6 +24,8 @@ SIGNATURES = {
     "hp_destroy": (_i, [_vp]),
     "hp_csr_nnz": (_i64, [_i]),
     "hp_assemble_csr": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "hp_strip_csr_nnz": (_i64, [_i, _i]),
+    "hp_assemble_strip_csr": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "hp_stencil_matvec": (_i, [_vp, _vp, _vp, _vp]),
     "hp_stencil_matvec_rows": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "hp_csr_matvec": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -104,6 +104,46 @@ __global__ void __launch_bounds__(HP_ASM_THREADS) hp_assemble_csr_kernel(int n, 
     }
 }
 
+// Strip operator H_m as sorted CSR (get_Hm, /root/reference/code.py:283-290): the 5-point operator of the b grid rows
+// m-b+1..m with the x2 PML moved to end on row m (s2m).  Row r = k n + (i-1) (k = 0..b-1 local grid row) holds the
+// couplings to (i, k-1), (i-1, k), itself, (i+1, k), (i, k+1); the entries the reference zeroes across the row ends
+// (c1_vec[n-1::n] = 0) and the ones outside the strip are not stored.  Thread -> grid column i: the coefficients come
+// from the same hp_strip_rows / hp_block_row the factorisation uses (csrc/hp_setup_core.h).
+__device__ __forceinline__ int64_t hp_strip_row_offset(int64_t r, int64_t nn, int64_t b) {
+    const int64_t k0 = r / nn, i0 = r - k0 * nn;
+    return 5 * r - (r < nn ? r : nn) - (r > (b - 1) * nn ? r - (b - 1) * nn : 0) - (k0 + (i0 > 0 ? 1 : 0)) - k0;
+}
+__global__ void hp_strip_csr_kernel(HpStripCtx c, int m, int32_t* __restrict__ indptr, int32_t* __restrict__ indices,
+                                    cplx* __restrict__ data) {
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;       // 0-based column
+    const int n = c.n, b = c.b;
+    if (i0 >= n) return;
+    HpStripRow R;
+    hp_strip_rows(R, m, b, c.pml);
+    HpBlockRow B;
+    hp_block_row(B, R, i0 + 1, m, b, n, c.pml, c.s1t, c.is1t, c.c_mat, c.omega2);
+    for (int k = 0; k < b; ++k) {
+        const int64_t r = (int64_t)k * n + i0;
+        int64_t o = hp_strip_row_offset(r, n, b);
+        indptr[r] = (int32_t)o;
+        if (k > 0)      { indices[o] = (int32_t)(r - n); data[o] = B.sub[k]; ++o; }
+        if (i0 > 0)     { indices[o] = (int32_t)(r - 1); data[o] = B.L[k]; ++o; }
+                          indices[o] = (int32_t)r;       data[o] = B.dia[k]; ++o;
+        if (i0 < n - 1) { indices[o] = (int32_t)(r + 1); data[o] = B.U[k]; ++o; }
+        if (k < b - 1)  { indices[o] = (int32_t)(r + n); data[o] = B.sup[k]; ++o; }
+        if (r == (int64_t)b * n - 1) indptr[r + 1] = (int32_t)o;
+    }
+}
+extern "C" int64_t hp_strip_csr_nnz(int n, int b) { return 5 * (int64_t)b * n - 2 * (int64_t)n - 2 * (int64_t)b; }
+extern "C" int hp_assemble_strip_csr(hp_solver* s, int m, int32_t* indptr_dev, int32_t* indices_dev, double* data_dev, void* stream) {
+    if (!s) { hp_set_error("hp_assemble_strip_csr: null solver"); return 1; }
+    if (m < s->b || m > s->n) { hp_set_error("hp_assemble_strip_csr: layer m must lie in %d..%d, got %d", s->b, s->n, m); return 1; }
+    hp_count_launch();
+    hp_strip_csr_kernel<<<(s->n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(hp_ctx(s), m, indptr_dev, indices_dev, (cplx*)data_dev);
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // Matrix-free y = A x.  A CTA owns 128 consecutive x1 columns and marches over HP_SPMV_ROWS grid rows;
 // each thread keeps the x2 neighbours (south, centre, north) of its column in registers, takes the x1
 // neighbours from the adjacent lanes by shuffle (warp-edge lanes read them from L1/L2) and keeps the

@@ -54,6 +54,21 @@ __device__ __forceinline__ void cmma(CFrag& c, cplx a, cplx b) {
     dmma884(c.p2[0], c.p2[1], a.y, b.y);
     dmma884(c.p3[0], c.p3[1], a.x + a.y, b.x + b.y);
 }
+// A dependent DMMA waits ~200 cycles for its accumulator (tools/micro/dmma.cu: one warp with 8 independent chains issues
+// one DMMA per 25 cycles), 12 times the 16 cycles it occupies the pipe: every product below runs its k-steps on
+// NST interleaved accumulator sets (3 NST independent chains) that are summed at the end.
+#define NST 4
+__device__ __forceinline__ void cfrag_zero4(CFrag (&c)[NST]) {
+#pragma unroll
+    for (int i = 0; i < NST; ++i) cfrag_zero(c[i]);
+}
+__device__ __forceinline__ cplx cfrag_get4(const CFrag (&c)[NST], int i) {
+    CFrag t;
+    t.p1[i] = (c[0].p1[i] + c[1].p1[i]) + (c[2].p1[i] + c[3].p1[i]);
+    t.p2[i] = (c[0].p2[i] + c[1].p2[i]) + (c[2].p2[i] + c[3].p2[i]);
+    t.p3[i] = (c[0].p3[i] + c[1].p3[i]) + (c[2].p3[i] + c[3].p3[i]);
+    return t.get(i);
+}
 __device__ __forceinline__ cplx cz() { return cmake(0.0, 0.0); }
 
 // MODE: 0 forward, 1 backward (reference diagonal), 2 backward (paper diagonal)
@@ -195,8 +210,8 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
                 }
             }
             // ---- x-independent part: the K partial sums of gl (DSMEM) and gf (L2, poll warp), split over the warps
-            CFrag acc[2];                                   // entry tiles 0, 1 (HP_BMAX <= 24 would need 3: see the host check)
-            cfrag_zero(acc[0]); cfrag_zero(acc[1]);
+            CFrag acc[2][2];                                // entry tiles 0, 1 (b <= 16: see the host check), two k-streams each
+            cfrag_zero(acc[0][0]); cfrag_zero(acc[0][1]); cfrag_zero(acc[1][0]); cfrag_zero(acc[1][1]);
             if (has_sep) {
                 mbar_wait4(&barGL[par], ph, abort_flag, dead);
                 mbar_wait_acq4(&barGF[par], ph, abort_flag, dead);
@@ -206,11 +221,11 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
                     if (t < ntile_e && e < b) {
                         for (int kk = cw; kk < K; kk += HP4_CW) {
                             const size_t o = (((size_t)par * K + kk) * b + e) * RT + 2 * ft;
-                            acc[t].add(0, glp[o]); acc[t].add(1, glp[o + 1]);
+                            acc[t][0].add(0, glp[o]); acc[t][0].add(1, glp[o + 1]);
                         }
                         if (cw == HP4_CW - 1) {
                             const size_t o = ((size_t)par * b + e) * RT + 2 * ft;
-                            acc[t].add(0, gfp[o]); acc[t].add(1, gfp[o + 1]);
+                            acc[t][0].add(0, gfp[o]); acc[t][0].add(1, gfp[o + 1]);
                         }
                     }
                 }
@@ -229,14 +244,17 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
                 // ---- B: P = R(it) X3(it-1): this warp's share of the 3b columns, both entry tiles
                 const cplx* R = reinterpret_cast<const cplx*>(ringR + par * pl.r_st);
                 if (it > 0) {
-                    for (int ks = cw * ks_per; ks < min(nks_b, (cw + 1) * ks_per); ++ks) {
-                        const int c = 4 * ks + ft;
-                        const cplx bv = c < b3 ? x3p[(size_t)fg * B3V + c] : cz();
+                    const int ks_end = min(nks_b, (cw + 1) * ks_per);
+                    for (int ks0 = cw * ks_per; ks0 < ks_end; ks0 += 2) {
 #pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            const int e = fg + 8 * t;
-                            const cplx av = (t < ntile_e && e < b && c < b3) ? R[(size_t)e * b3 + c] : cz();
-                            cmma(acc[t], av, bv);
+                        for (int j = 0; j < 2; ++j) {
+                            const int c = 4 * (ks0 + j) + ft;
+                            const bool on = ks0 + j < ks_end && c < b3;
+                            const cplx bv = on ? x3p[(size_t)fg * B3V + c] : cz();
+                            const cplx a0 = (on && fg < b) ? R[(size_t)fg * b3 + c] : cz();
+                            const cplx a1 = (on && ntile_e > 1 && fg + 8 < b) ? R[(size_t)(fg + 8) * b3 + c] : cz();
+                            cmma(acc[0][j], a0, bv);
+                            cmma(acc[1][j], a1, bv);
                         }
                     }
                 }
@@ -245,7 +263,7 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
                 for (int t = 0; t < 2; ++t) {
                     const int e = fg + 8 * t;
                     if (t < ntile_e && e < b) {
-                        cplx r0 = acc[t].get(0), r1 = acc[t].get(1);
+                        cplx r0 = cadd(acc[t][0].get(0), acc[t][1].get(0)), r1 = cadd(acc[t][0].get(1), acc[t][1].get(1));
                         if (is_sep && t == sep_tile) { r0 = csub(r0, vsb[0]); r1 = csub(r1, vsb[1]); }
                         rho_p[((size_t)cw * RT + 2 * ft) * BV + e] = r0;
                         rho_p[((size_t)cw * RT + 2 * ft + 1) * BV + e] = r1;
@@ -268,9 +286,9 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
                 // ---- C: own rows of X(it) = N[:, sep l] Rho: row tiles round robin over the warps
                 if (nrq_own > 0) mbar_wait4(&barN[par], ph, abort_flag, dead);
                 const cplx* Np = reinterpret_cast<const cplx*>(ringN + par * pl.n_st);          // [b][NRQV]
-                cplx bq[6];                                  // B fragments of the k-steps (b <= 24)
+                cplx bq[NST];                                // B fragments of the k-steps (b <= 16)
 #pragma unroll
-                for (int ks = 0; ks < 6; ++ks) {
+                for (int ks = 0; ks < NST; ++ks) {
                     const int c = 4 * ks + ft;
                     cplx s = cz();
                     if (ks < nks_c && c < b) {
@@ -284,26 +302,26 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
                     const int tr1 = tr0 + HP4_CW;
                     const int row0 = 32 * (tr0 >> 2) + 4 * fg + (tr0 & 3);
                     const int row1 = tr1 < ntile_r ? 32 * (tr1 >> 2) + 4 * fg + (tr1 & 3) : nrq_own;
-                    CFrag xa, xb;
-                    cfrag_zero(xa); cfrag_zero(xb);
+                    CFrag xa[NST], xb[NST];                      // one accumulator set per k-step (b <= 16: at most 4)
+                    cfrag_zero4(xa); cfrag_zero4(xb);
 #pragma unroll
-                    for (int ks = 0; ks < 6; ++ks) {
+                    for (int ks = 0; ks < NST; ++ks) {
                         const int c = 4 * ks + ft;
                         if (ks < nks_c) {                      // warp-uniform
                             const cplx a0 = (row0 < nrq_own && c < b) ? Np[(size_t)c * NRQV + row0] : cz();
                             const cplx a1 = (row1 < nrq_own && c < b) ? Np[(size_t)c * NRQV + row1] : cz();
-                            cmma(xa, a0, bq[ks]);
-                            cmma(xb, a1, bq[ks]);
+                            cmma(xa[ks], a0, bq[ks]);
+                            cmma(xb[ks], a1, bq[ks]);
                         }
                     }
                     if (row0 < nrq_own) {
                         const size_t o = a.oXS + ((size_t)(NRQ * k + row0) * PP + l) * RT + 2 * ft;
-                        xput(slot + o, xa.get(0)); xput(slot + o + 1, xa.get(1));
+                        xput(slot + o, cfrag_get4(xa, 0)); xput(slot + o + 1, cfrag_get4(xa, 1));
                         xarm(slot_next + o); xarm(slot_next + o + 1);
                     }
                     if (row1 < nrq_own) {
                         const size_t o = a.oXS + ((size_t)(NRQ * k + row1) * PP + l) * RT + 2 * ft;
-                        xput(slot + o, xb.get(0)); xput(slot + o + 1, xb.get(1));
+                        xput(slot + o, cfrag_get4(xb, 0)); xput(slot + o + 1, cfrag_get4(xb, 1));
                         xarm(slot_next + o); xarm(slot_next + o + 1);
                     }
                 }
@@ -380,7 +398,7 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
             for (int i = 0; i < 2; ++i) sep_output(m0 + itl * step, i, x3[((size_t)(itl & 1) * RT + 2 * ft + i) * B3V + b2 - 1]);
         }
         if (DBG && tid == 0)
-            for (int i = 0; i < 8; ++i) a.dbg[(size_t)g_ * 16 + i] = tacc[i];
+            for (int i = 0; i < 6; ++i) a.dbg[(size_t)g_ * 16 + i] = tacc[i];
     } else if (tid < HP4_CRIT + HP4_PROD) {
         // =====================================================================================================
         // producer warp: every TMA copy of the sweep.  The columns of N go to rows of NRQV (padded) complex numbers.
@@ -475,24 +493,31 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
                     else if (more) unx[i] = ldcg(u + (size_t)(mn - 1) * n + c);
                 }
             }
-            if (DBG && ot == 0) tprev = clock64();
+            if (DBG && (ot == 0 || ot == 128)) tprev = clock64();
+#define HPD_TICK4(i) do { if (DBG && ot == 128) { long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
             if (!owner) {
                 // ---- a (warps 4-7): Gb(t) = Gc(t) Vb(t): row tile ow - 4 of the 2b interface components (4 tiles cover b <= 16;
                 //      larger b: a second pass), gf -> cluster l-1 (L2), gl -> every CTA of the cluster (DSMEM)
                 if (live) {
                     mbar_wait4(&barG[it % 3], (it / 3) & 1, abort_flag, dead);
+                    HPD_TICK4(0);
                     if (any_sep) {
                         for (int kap0 = 0; kap0 < b2; kap0 += 32) {
                             const int kap = kap0 + 4 * fg + (ow & 3);
-                            CFrag gb;
-                            cfrag_zero(gb);
-                            for (int ks = 0; ks < nks_g; ++ks) {
-                                const int cc = 4 * ks + ft;
-                                const cplx av = (kap < b2 && cc < ncols) ? Gp[(size_t)kap * CW + cc] : cz();
-                                const cplx bv = cc < ncols ? vb[(size_t)fg * CWV + cc] : cz();
-                                cmma(gb, av, bv);
+                            CFrag gb[NST];
+                            cfrag_zero4(gb);
+                            for (int ks0 = 0; ks0 < nks_g; ks0 += NST) {
+                                cplx av[NST], bv[NST];
+#pragma unroll
+                                for (int j = 0; j < NST; ++j) {
+                                    const int cc = 4 * (ks0 + j) + ft;
+                                    av[j] = (kap < b2 && cc < ncols) ? Gp[(size_t)kap * CW + cc] : cz();
+                                    bv[j] = cc < ncols ? vb[(size_t)fg * CWV + cc] : cz();
+                                }
+#pragma unroll
+                                for (int j = 0; j < NST; ++j) cmma(gb[j], av[j], bv[j]);
                             }
-                            const cplx r0 = gb.get(0), r1 = gb.get(1);
+                            const cplx r0 = cfrag_get4(gb, 0), r1 = cfrag_get4(gb, 1);
                             if (kap < b) {
                                 if (l > 0) {
                                     const size_t o = a.oGP + (((size_t)l * K + k) * b + kap) * RT + 2 * ft;
@@ -515,6 +540,7 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
                     if (lane == 0) mbar_arrive_local(&eG[(it + 2) % 3]);
                 }
                 if (!live) break;
+                HPD_TICK4(1);
                 // ---- the gf partials of leaf l+1 for this strip ([K][b][RT] self-validating words in L2, written by the same
                 //      phase of the clusters on the right): warps 4..6 sum the K parts of 32 outputs each and hand them to the
                 //      critical group in shared memory
@@ -549,25 +575,31 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
                     __syncwarp();
                     if (lane == 0) mbar_arrive_rel4(&barGF[par]);
                 }
+                HPD_TICK4(2);
             } else {
                 // ---- b (warps 0-3): x3(t-1) arrives: correction C = Gc(t-1)^T [x_{l-1}; x_l], finish strip t-1 on the own
                 //      columns, input of strip t to every CTA of the leaf
                 cplx v[2] = {vbr[0], vbr[1]};
                 if (it > 0) {
-                    CFrag cr;
-                    cfrag_zero(cr);
+                    CFrag cr[NST];
+                    cfrag_zero4(cr);
                     if (any_sep) {
                         mbar_wait4(&barX[par ^ 1], ((it - 1) >> 1) & 1, abort_flag, dead);
                         HPD_TICK(2);
                         const cplx* xa = x3 + (size_t)(par ^ 1) * RT * B3V;
-                        for (int ks = 0; ks < nks_x; ++ks) {
-                            const int kap = 4 * ks + ft;
-                            const cplx av = (oc < ncols && kap < b2) ? Gprev[(size_t)kap * CW + oc] : cz();
-                            const cplx bv = kap < b2 ? xa[(size_t)fg * B3V + kap] : cz();
-                            cmma(cr, av, bv);
+                        for (int ks0 = 0; ks0 < nks_x; ks0 += NST) {
+                            cplx av[NST], bv[NST];
+#pragma unroll
+                            for (int j = 0; j < NST; ++j) {
+                                const int kap = 4 * (ks0 + j) + ft;
+                                av[j] = (oc < ncols && kap < b2) ? Gprev[(size_t)kap * CW + oc] : cz();
+                                bv[j] = kap < b2 ? xa[(size_t)fg * B3V + kap] : cz();
+                            }
+#pragma unroll
+                            for (int j = 0; j < NST; ++j) cmma(cr[j], av[j], bv[j]);
                         }
                     }
-                    const cplx corr[2] = {cr.get(0), cr.get(1)};
+                    const cplx corr[2] = {cfrag_get4(cr, 0), cfrag_get4(cr, 1)};
                     if (col) {
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
@@ -596,29 +628,34 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
             // ---- c: leaf product Y0(t) = W(t) V_leaf(t) on the tensor cores: all chunks of the strip are resident
             mbar_wait4(&barV[par], ph, abort_flag, dead);
             HPD_TICK(4);
+            HPD_TICK4(3);
             for (int ch = 0; ch < NCH; ++ch) mbar_wait4(&barW[(it * NCH + ch) % S], ((it * NCH + ch) / S) & 1, abort_flag, dead);
+            HPD_TICK(7);
             {
                 const cplx* vl = v_leaf + (size_t)par * RT * QPV;
                 const int wch = wrow / RC;
                 const cplx* wr = reinterpret_cast<const cplx*>(ringW + (size_t)((it * NCH + wch) % S) * pl.w_st) + (size_t)(wrow - wch * RC) * QP;
                 const bool rowok = wrow < ncols;
-                CFrag y, y2;                                 // even / odd k-steps: 8 independent DMMA chains
-                cfrag_zero(y); cfrag_zero(y2);
-                for (int ks = ks_lo; ks < ks_hi; ks += 2) {
-                    const int cq = 4 * ks + ft, cq2 = cq + 4;
-                    const bool k2 = ks + 1 < ks_hi;
-                    const cplx av = (rowok && cq < q) ? wr[cq] : cz();
-                    const cplx bv = cq < q ? vl[(size_t)fg * QPV + cq] : cz();
-                    const cplx av2 = (rowok && k2 && cq2 < q) ? wr[cq2] : cz();
-                    const cplx bv2 = (k2 && cq2 < q) ? vl[(size_t)fg * QPV + cq2] : cz();
-                    cmma(y, av, bv);
-                    cmma(y2, av2, bv2);
+                CFrag y[NST];
+                cfrag_zero4(y);
+                for (int ks0 = ks_lo; ks0 < ks_hi; ks0 += NST) {
+                    cplx av[NST], bv[NST];
+#pragma unroll
+                    for (int j = 0; j < NST; ++j) {
+                        const int cq = 4 * (ks0 + j) + ft;
+                        const bool on = ks0 + j < ks_hi && cq < q;
+                        av[j] = (on && rowok) ? wr[cq] : cz();
+                        bv[j] = on ? vl[(size_t)fg * QPV + cq] : cz();
+                    }
+#pragma unroll
+                    for (int j = 0; j < NST; ++j) cmma(y[j], av[j], bv[j]);
                 }
                 if (rowok) {
-                    y0p[((size_t)(ow >> 2) * RT + 2 * ft) * CWV + wrow] = cadd(y.get(0), y2.get(0));
-                    y0p[((size_t)(ow >> 2) * RT + 2 * ft + 1) * CWV + wrow] = cadd(y.get(1), y2.get(1));
+                    y0p[((size_t)(ow >> 2) * RT + 2 * ft) * CWV + wrow] = cfrag_get4(y, 0);
+                    y0p[((size_t)(ow >> 2) * RT + 2 * ft + 1) * CWV + wrow] = cfrag_get4(y, 1);
                 }
             }
+            HPD_TICK(0);
             __syncwarp();
             if (lane == 0)
                 for (int ch = 0; ch < NCH; ++ch) mbar_arrive_local(&eW[(it * NCH + ch) % S]);
@@ -643,9 +680,17 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
             }
             bar_off4();                                      // vb ready, y0p free for the next strip
             HPD_TICK(6);
+            HPD_TICK4(4);
         }
-        if (DBG && ot == 0)
-            for (int i = 0; i < 8; ++i) a.dbg[(size_t)g_ * 16 + 8 + i] = tacc[i];
+        if (DBG && ot == 0) {
+            for (int i = 2; i < 8; ++i) a.dbg[(size_t)g_ * 16 + 8 + i] = tacc[i];
+            a.dbg[(size_t)g_ * 16 + 6] = tacc[0];            // leaf product proper (loads + DMMA + store)
+        }
+        if (DBG && ot == 128) {              // warp 4: G wait, interface product, gf poll, wait V, leaf product + tail barriers
+            a.dbg[(size_t)g_ * 16 + 7] = tacc[0] + tacc[1] + tacc[2];
+            a.dbg[(size_t)g_ * 16 + 8 + 0] = tacc[3];
+            a.dbg[(size_t)g_ * 16 + 8 + 1] = tacc[4];
+        }
     }
     __syncthreads();
     cluster_sync_all();

@@ -97,6 +97,18 @@ class HelmholtzSolver:
                    "hp_assemble_csr")
         return DeviceCSR(self, indptr, indices, data)
 
+    def assemble_strip_csr(self, m):
+        """get_Hm(m): the strip operator of layer m as sorted CSR on the device (code.py:283-290)."""
+        self._on_device()
+        n, b = self.n, self.b
+        nnz = self.lib.hp_strip_csr_nnz(n, b)
+        indptr = torch.empty(b * n + 1, dtype=torch.int32, device=self.device)
+        indices = torch.empty(nnz, dtype=torch.int32, device=self.device)
+        data = torch.empty(nnz, dtype=torch.complex128, device=self.device)
+        _lib.check(self.lib.hp_assemble_strip_csr(self.handle, int(m), _ptr(indptr), _ptr(indices), _ptr(data), _stream()),
+                   "hp_assemble_strip_csr")
+        return DeviceCSR(self, indptr, indices, data, shape=(b * n, b * n))
+
     def matvec(self, x, out=None):
         """y = A x, matrix free."""
         self._on_device()
@@ -301,9 +313,9 @@ class HelmholtzSolver:
 class DeviceCSR:
     """What build_A_matrix returns: the operator as sorted CSR arrays in device memory."""
 
-    def __init__(self, solver, indptr, indices, data):
+    def __init__(self, solver, indptr, indices, data, shape=None):
         self.solver, self.indptr, self.indices, self.data = solver, indptr, indices, data
-        self.shape = (solver.n ** 2, solver.n ** 2)
+        self.shape = shape if shape is not None else (solver.n ** 2, solver.n ** 2)
 
     def matvec(self, x, out=None):
         x = _as_device_field(x, self.solver.device)
@@ -332,6 +344,27 @@ def _solver_for(b, const, eta, omega, h, n, c_mat, device=None):
 def build_A_matrix(b, const, eta, omega, h, n, c_mat, device=None):
     """code.py:202-219."""
     return _solver_for(b, const, eta, omega, h, n, c_mat, device).assemble_csr()
+
+
+def get_Hm(m, b, const, eta, omega, h, n, c_mat, device=None):
+    """code.py:283-290: the strip operator of layer m (DeviceCSR, bn x bn)."""
+    return _solver_for(b, const, eta, omega, h, n, c_mat, device).assemble_strip_csr(m)
+
+
+def get_A_FF_block(b, const, eta, omega, h, n, c_mat, device=None, coupled=False):
+    """code.py:178-183.  The reference keeps only the diagonal blocks (b tridiagonal systems); coupled=True is the full
+    A[:bn, :bn] = get_Hm(b).  Returned as DeviceCSR; the block-diagonal form drops the couplings between the rows."""
+    A = _solver_for(b, const, eta, omega, h, n, c_mat, device).assemble_strip_csr(b)
+    if coupled:
+        return A
+    indptr, indices, data = A.to_host()
+    rows = np.repeat(np.arange(b * n), np.diff(indptr))
+    keep = np.abs(indices - rows) <= 1                              # code.py:180-182: block_diag of the A_ii
+    ip = np.zeros(b * n + 1, dtype=np.int32)
+    np.cumsum(np.bincount(rows[keep], minlength=b * n), out=ip[1:])
+    dev = A.solver.device
+    return DeviceCSR(A.solver, torch.from_numpy(ip).to(dev), torch.from_numpy(indices[keep]).to(dev),
+                     torch.from_numpy(data[keep]).to(dev), shape=A.shape)
 
 
 def algo2_3(b, const, eta, omega, h, n, c_mat, device=None, P=0, K=0, layout="auto", front="blockdiag"):

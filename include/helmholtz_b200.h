@@ -48,6 +48,12 @@ int64_t hp_csr_nnz(int n);
 /* build_A_matrix (code.py:202-219, with get_A_diag_block_coeffs :71-115, get_upper/lower_A_block :131-154):
  * writes sorted CSR, indptr[n*n+1] and indices[nnz] int32 (scipy's index type here), data[nnz] complex128. */
 int hp_assemble_csr(hp_solver* s, int32_t* indptr_dev, int32_t* indices_dev, double* data_dev, void* stream);
+/* get_Hm (code.py:283-290, with get_Hm_coeffs :224-279): the bn x bn operator of the b grid rows m-b+1..m with the x2
+ * PML moved to end on row m, as sorted CSR (indptr[b*n+1], indices/data[hp_strip_csr_nnz]); b <= m <= n.  m = b is the
+ * coupled front block A[:bn, :bn].  algo2_3 does not go through this matrix (the strips are factored from the same
+ * coefficients in block form); it is the reference's helper, exposed for inspection and tests. */
+int64_t hp_strip_csr_nnz(int n, int b);
+int hp_assemble_strip_csr(hp_solver* s, int m, int32_t* indptr_dev, int32_t* indices_dev, double* data_dev, void* stream);
 /* y = A x without forming A (the matvec scipy's gmres performs at code.py:516, iterative.py `matvec`) */
 int hp_stencil_matvec(hp_solver* s, const double* x_dev, double* y_dev, void* stream);
 /* the same for the grid rows j_lo <= j < j_hi (0-based) of a slab: x_dev/y_dev hold those rows only, x_south_dev /

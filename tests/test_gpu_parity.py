@@ -56,6 +56,34 @@ def test_assembly_golden(hp, path):
     assert relerr(y2, g["A_x_rand"]) < 1e-13
 
 
+@pytest.mark.parametrize("path", CASES, ids=IDS)
+def test_strip_operator_csr_golden(hp, path):
+    """get_Hm on the device (code.py:283-290): sparsity pattern bit exact, values to 1e-12, against the unmodified
+    reference's first / middle / last layer; the moving-PML coefficients the factorisation is built from."""
+    import scipy.sparse
+    g, p = _load(path)
+    for tag in ("first", "mid", "last"):
+        m = int(g[f"Hm_{tag}_m"])
+        H = hp.get_Hm(m, c_mat=g["c_mat"], **p)
+        indptr, indices, data = H.to_host()
+        assert np.array_equal(indptr, g[f"Hm_{tag}_indptr"])
+        assert np.array_equal(indices, g[f"Hm_{tag}_indices"])
+        assert np.max(np.abs(data - g[f"Hm_{tag}_data"]) / np.abs(g[f"Hm_{tag}_data"])) < 1e-12
+    # the front block: get_Hm(b) is A[:bn, :bn]; the reference's H_F keeps its tridiagonal diagonal blocks
+    b, n = p["b"], p["n"]
+    A = scipy.sparse.csr_matrix((g["A_data"], g["A_indices"], g["A_indptr"]), shape=(n * n, n * n))[:b * n, :b * n].tocsr()
+    A.sort_indices()
+    ip, ix, d = hp.get_A_FF_block(c_mat=g["c_mat"], coupled=True, **p).to_host()
+    assert np.array_equal(ip, A.indptr) and np.array_equal(ix, A.indices)
+    assert np.max(np.abs(d - A.data) / np.abs(A.data)) < 1e-12
+    HF = orc.get_A_FF_block(c_mat=g["c_mat"], **p).tocsr()
+    HF.sort_indices()
+    HF.eliminate_zeros()
+    ip, ix, d = hp.get_A_FF_block(c_mat=g["c_mat"], **p).to_host()
+    assert np.array_equal(ip, HF.indptr) and np.array_equal(ix, HF.indices)
+    assert np.max(np.abs(d - HF.data) / np.abs(HF.data)) < 1e-12
+
+
 @pytest.mark.parametrize("layout", ["classic", "cluster"])
 @pytest.mark.parametrize("n,b,P,K", [(45, 12, 4, 2), (63, 12, 5, 3), (40, 5, 1, 3), (40, 5, 7, 1), (50, 20, 3, 4)])
 def test_strip_generators_vs_model(hp, n, b, P, K, layout):

@@ -13,8 +13,8 @@ s = hp.HelmholtzSolver(n, b, omega, 100.0, c_mat).setup_preconditioner()
 L = s.layout()
 g = torch.Generator(device="cuda").manual_seed(1)
 xs = [torch.randn(n * n, dtype=torch.complex128, device="cuda", generator=g) for _ in range(8)]
-names = ["pre (GL,GF,R)", "A wait x3", "B rho+bar", "C rows", "D poll", "D sum+send", "-", "-",
-         "a G wait", "a gb", "b wait x3", "b corr+send", "c wait V", "c W", "c tail", "(W chunk waits)"]
+names = ["pre (GL,GF,R)", "A wait x3", "B rho+bar", "C rows", "D poll", "D sum+send", "c W compute only", "w4: G wait + a + poll",
+         "w4: wait V", "w4: W + tail bars", "b wait x3", "b corr+send", "c wait V", "c W barrier", "c tail", "(W chunk waits)"]
 nst = n - 1 - b
 for R in Rs:
     bufs = [x.clone() for x in xs[:R]]
