@@ -11,6 +11,7 @@ PyTorch is used for device buffers and streams only; every n^2-sized operation i
 There is no CPU path: without the library or a CUDA device these functions raise.
 """
 import ctypes as C
+import os
 import time
 from dataclasses import dataclass, field
 
@@ -232,8 +233,9 @@ class HelmholtzSolver:
         return g
 
     def batch_kernel_name(self, R):
-        if self.batch_group(R) > 1:
-            return "hp_sweep4m_kernel"
+        g = self.batch_group(R)
+        if g > 1:
+            return "hp_sweep4d_kernel (FP64 tensor cores, 8 right-hand sides)" if g == 8 and not os.environ.get("HP_NO_DMMA") else "hp_sweep4m_kernel"
         return "hp_sweep4_kernel" if self.layout()["colN"] else "hp_sweep2_kernel"
 
     @staticmethod
