@@ -10,6 +10,7 @@
 // hp_tables_kernel) and the per-point work is a handful of complex multiplies: both kernels below are
 // HBM-bound (CSR: 104 B written per row; matvec: 40 B per grid point).
 #include "hp_internal.cuh"
+#include <stdlib.h>
 
 __global__ void hp_tables_kernel(int n, HpPml p, cplx* s1t, cplx* is1t, cplx* s2t, cplx* is2t) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -149,17 +150,20 @@ extern "C" int hp_assemble_strip_csr(hp_solver* s, int m, int32_t* indptr_dev, i
 // neighbours from the adjacent lanes by shuffle (warp-edge lanes read them from L1/L2) and keeps the
 // x1-dependent factors in registers for the whole march.  Algorithmic traffic per grid point:
 // x 16 B read + y 16 B written + kappa 8 B read = 40 B.
-#define HP_SPMV_ROWS 16
+// The march length (rows per CTA) is chosen by the host so that the whole grid is ONE wave of resident CTAs
+// (hp_spmv_rows): with a fixed 16 rows the 8192 CTAs of 4096^2 ran as 6.9 waves of 1184 and the last, partly filled
+// wave cost 7 % of the kernel; longer marches also read fewer halo rows twice (2 per march).
+#define HP_SPMV_MIN_ROWS 16
 // Rows j_lo <= j < j_hi (0-based) of the grid: x and y hold those rows only (slab storage); the rows just
 // outside come from the halo pointers x_south (row j_lo-1) and x_north (row j_hi), NULL on the grid boundary.
-__global__ void __launch_bounds__(128) hp_stencil_matvec_kernel(int n, int j_lo, int j_hi, double ih2, cplx omega2,
+__global__ void __launch_bounds__(128) hp_stencil_matvec_kernel(int n, int j_lo, int j_hi, int rows, int pf, double ih2, cplx omega2,
         const cplx* __restrict__ s1t, const cplx* __restrict__ is1t, const cplx* __restrict__ s2t,
         const cplx* __restrict__ is2t, const double* __restrict__ kappa,
         const cplx* __restrict__ x, const cplx* __restrict__ x_south, const cplx* __restrict__ x_north,
         cplx* __restrict__ y) {
     const int col = blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const int j0 = j_lo + blockIdx.y * HP_SPMV_ROWS;
+    const int j0 = j_lo + blockIdx.y * rows;
     const bool act = col < n;
     const cplx zero = cmake(0.0, 0.0);
     cplx aW = zero, aE = zero, dI = zero, wI = zero;
@@ -175,11 +179,18 @@ __global__ void __launch_bounds__(128) hp_stencil_matvec_kernel(int n, int j_lo,
         else if (x_south) xS = x_south[col];
     }
     cplx xC = act ? x[(size_t)(j0 - j_lo) * n + col] : zero;
+    const int j1 = min(j_hi, j0 + rows);
 #pragma unroll 4
-    for (int r = 0; r < HP_SPMV_ROWS; ++r) {
-        const int j = j0 + r;                       // 0-based grid row, uniform over the CTA
-        if (j >= j_hi) break;
+    const int pcols = min(128, n - (int)blockIdx.x * 128);
+    for (int j = j0; j < j1; ++j) {                 // 0-based grid row, uniform over the CTA
         const size_t base = (size_t)(j - j_lo) * n;
+        // HBM -> L2 a few rows ahead of the march (one bulk prefetch per row segment): the demand loads below then
+        // wait for an L2 hit instead of a DRAM access, and a third of the bytes in flight per SM sustain the same bandwidth
+        if (pf > 0 && threadIdx.x == 0 && j + pf < j1) {
+            if (j + pf + 1 < j_hi)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + base + (size_t)(pf + 1) * n + blockIdx.x * 128), "r"(pcols * 16) : "memory");
+            if ((n & 1) == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kappa + (size_t)(j + pf) * n + blockIdx.x * 128), "r"(pcols * 8) : "memory");
+        }
         cplx xN = zero;
         if (act) {
             if (j + 1 < j_hi) xN = x[base + n + col];
@@ -231,14 +242,39 @@ extern "C" int hp_assemble_csr(hp_solver* s, int32_t* indptr, int32_t* indices, 
     return 0;
 }
 
+// rows per CTA such that the grid fills the resident CTA slots of the device once (HP_SPMV_ROWS overrides)
+static int hp_spmv_rows(int n, int nrows) {
+    static int slots = 0, forced = -1;
+    if (forced < 0) { const char* e = getenv("HP_SPMV_ROWS"); forced = e ? atoi(e) : 0; }
+    if (forced > 0) return forced;
+    if (!slots) {
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hp_stencil_matvec_kernel, 128, 0) == cudaSuccess && per_sm > 0)
+            slots = sms * per_sm;
+        else { cudaGetLastError(); slots = 1184; }
+    }
+    const int colblocks = (n + 127) / 128;
+    const int rowblocks = slots / colblocks > 0 ? slots / colblocks : 1;
+    const int rows = (nrows + rowblocks - 1) / rowblocks;
+    return rows < HP_SPMV_MIN_ROWS ? HP_SPMV_MIN_ROWS : rows;
+}
+
+static int hp_spmv_pf() {
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("HP_SPMV_PF"); pf = e ? atoi(e) : 3; }
+    return pf;
+}
+
 extern "C" int hp_stencil_matvec_rows(hp_solver* s, int j_lo, int j_hi, const double* x, const double* x_south,
                                       const double* x_north, double* y, void* stream) {
     if (!s) { hp_set_error("hp_stencil_matvec: null solver"); return 1; }
     if (j_lo < 0 || j_hi > s->n || j_lo >= j_hi) { hp_set_error("hp_stencil_matvec_rows: bad row range %d..%d", j_lo, j_hi); return 1; }
     double ih2 = 1.0 / (s->pml.h * s->pml.h);
-    dim3 grd((s->n + 127) / 128, (j_hi - j_lo + HP_SPMV_ROWS - 1) / HP_SPMV_ROWS);
+    const int rows = hp_spmv_rows(s->n, j_hi - j_lo);
+    dim3 grd((s->n + 127) / 128, (j_hi - j_lo + rows - 1) / rows);
     hp_count_launch(); hp_stencil_matvec_kernel<<<grd, 128, 0, (cudaStream_t)stream>>>(
-        s->n, j_lo, j_hi, ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa, (const cplx*)x,
+        s->n, j_lo, j_hi, rows, hp_spmv_pf(), ih2, s->omega2, s->s1t, s->is1t, s->s2t, s->is2t, s->kappa, (const cplx*)x,
         (const cplx*)x_south, (const cplx*)x_north, (cplx*)y);
     HP_CUDA(cudaGetLastError());
     return 0;
