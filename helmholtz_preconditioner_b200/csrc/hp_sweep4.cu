@@ -112,10 +112,20 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
 
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
 #define HP_TICK(i) do { if (DBG && lane == 0 && (tid == 0 || tid == HP4_CRIT + HP4_PROD)) { long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; } } while (0)
-    // timeline window: globaltimer stamps of strips 512..575, 8 per group, [G][64][16] behind the [G][16] phase sums
-#define HP_STAMP4(kk) do { if (DBG && (tid == 0 || tid == HP4_CRIT + HP4_PROD) && it >= 512 && it < 576) { unsigned long long t_; \
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
-        a.dbg[(size_t)a.lay.G * 16 + ((size_t)g * 64 + (it - 512)) * 16 + (tid == 0 ? 0 : 8) + (kk)] = (long long)t_; } } while (0)
+    // timeline window: globaltimer stamps (low 32 bits, ns) of HP4_LOG_STRIPS strips, 8 per group, kept in a shared-memory log while the sweep
+    // runs (a store to shared memory per event: globaltimer reads and global stores perturbed the period by 10-30 %) and
+    // written behind the [G][16] phase sums as [G][64][16] when the sweep is over; row 63 holds (globaltimer, clock64)
+    // pairs of the start and the end of the kernel, from which the host aligns the clocks of the SMs
+    unsigned int* slog = (DBG && pl.log_off) ? reinterpret_cast<unsigned int*>(smem_raw + pl.log_off) : nullptr;
+    const int win0 = pl.win0;
+    unsigned long long gt0 = 0; long long ck0 = 0;
+    if (DBG && slog) {
+        for (int i = tid; i < HP4_LOG_STRIPS * 16; i += HP4_THREADS) slog[i] = 0u;
+        __syncthreads();
+        if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); ck0 = clock64(); }
+    }
+#define HP_STAMP4(kk) do { if (DBG && slog && (tid == 0 || tid == HP4_CRIT + HP4_PROD) && (unsigned)(it - win0) < (unsigned)HP4_LOG_STRIPS) \
+        { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); slog[(it - win0) * 16 + (tid == 0 ? 0 : 8) + (kk)] = (unsigned int)t_; } } while (0)
 
     if (tid < HP4_CRIT) {
         // =====================================================================================================
@@ -269,6 +279,9 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                     }
                     // all loads of a round are issued back to back; the warp leaves the loop as a whole
                     unsigned int spins = 0;
+#ifdef HP4_EXP_POLLSTAMP
+                    HP_STAMP4(7);
+#endif
                     for (;;) {
                         unsigned long long lo[HP4_EW][HP4_PL], hi[HP4_EW][HP4_PL];
 #pragma unroll
@@ -286,10 +299,14 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                                 ok = ok && xvalid(lo[o][pp], hi[o][pp]);
                                 val[o][pp] = cmake(__longlong_as_double((long long)lo[o][pp]), __longlong_as_double((long long)hi[o][pp]));
                             }
+#ifdef HP4_EXP_POLLSTAMP
+                        if (spins == 0) HP_STAMP4(6);
+#endif
                         if (__all_sync(0xffffffffu, ok || *dead)) break;
                         if (++spins > HP_SPIN_LIMIT) { hp_raise_abort(abort_flag); *dead = 1u; }
                         if ((spins & 0xFFF) == 0 && *((volatile unsigned int*)abort_flag)) *dead = 1u;
                     }
+                    if (DBG && tid == 0) tacc[6] += spins + 1;          // polling rounds of warp 0
                     HP_TICK(4);
                     HP_STAMP4(5);
                     cplx sums[HP4_EW];
@@ -300,7 +317,9 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                         for (int pp = 1; pp < HP4_PL; ++pp) sacc = cadd(sacc, val[o][pp]);
                         sums[o] = hp_warp_sum2(sacc);
                     }
+#ifndef HP4_EXP_POLLSTAMP
                     HP_STAMP4(6);
+#endif
 #pragma unroll
                     for (int o = 0; o < HP4_EW; ++o) {
                         const int tt = tb + cw + HP4_CW * o;
@@ -310,7 +329,9 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                     }
                 }
                 HP_TICK(5);
+#ifndef HP4_EXP_POLLSTAMP
                 HP_STAMP4(7);
+#endif
             }
         }
         // output of the last strip on the separator column
@@ -349,6 +370,9 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                 for (int ch = 0; ch < NCH; ++ch) {
                     const int cidx = it * NCH + ch, sl = cidx % S, r0 = ch * RC;
                     if (cidx >= S) mbar_wait4(&eW[sl], ((cidx / S) - 1) & 1, abort_flag, dead);
+#ifdef HP4_EXP_NOW          // timing experiment (wrong results): W is copied once per ring slot
+                    if (cidx >= S) { mbar_arrive_local(&barW[sl]); continue; }
+#endif
                     ring_fill4(ringW + (size_t)sl * pl.w_st, pk_base + so * strip_stride + (size_t)r0 * QP,
                                (unsigned int)((size_t)min(RC, CW - r0) * QP * sizeof(cplx)), &barW[sl]);
                 }
@@ -556,7 +580,11 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                 if (DBG && ot == 0) tacc[7] += clock64() - tw0;
                 const cplx* Wc = reinterpret_cast<const cplx*>(ringW + (size_t)sl * pl.w_st);
                 cplx acc = cmake(0.0, 0.0), a1 = cmake(0.0, 0.0), a2 = cmake(0.0, 0.0), a3 = cmake(0.0, 0.0);
+#ifdef HP4_EXP_NOWV          // timing experiment (wrong results): no leaf product
+                if (false) {
+#else
                 if (r0 + wr_r < ncols) {
+#endif
                     const cplx* wr = Wc + (size_t)wr_r * QP;
                     int cq = wr_cp;
                     for (; cq + 3 * LPR < q; cq += 4 * LPR) {
@@ -603,6 +631,14 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
     }
     // no CTA leaves while a peer may still write into its shared memory
     __syncthreads();
+    if (DBG && slog) {
+        long long* tl = a.dbg + (size_t)a.lay.G * 16 + (size_t)g * 64 * 16;
+        for (int i = tid; i < HP4_LOG_STRIPS * 16; i += HP4_THREADS) tl[i] = (long long)slog[i];
+        if (tid == 0) {
+            unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+            tl[63 * 16 + 0] = (long long)gt0; tl[63 * 16 + 1] = ck0; tl[63 * 16 + 2] = (long long)gt1; tl[63 * 16 + 3] = clock64();
+        }
+    }
     cluster_sync_all();
 }
 
@@ -711,6 +747,14 @@ int hp_sweep4_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st) {
     at[1].id = cudaLaunchAttributeCooperative;
     at[1].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 2;
+    pl.log_off = 0; pl.win0 = 0;
+    if (a.dbg && pl.total + HP4_LOG_BYTES <= (size_t)max_smem) {
+        pl.log_off = pl.total; pl.total += HP4_LOG_BYTES;
+        const char* e = getenv("HP_DBG_WIN");
+        pl.win0 = e ? atoi(e) : 512;
+        HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
+        cfg.dynamicSmemBytes = pl.total;
+    }
     void* args[] = {&a, &pl};
     // cooperative = the driver checks that all clusters are co-resident (the CTAs exchange data by spinning on L2 words
     // and mbarriers).  Kernel-replaying profilers (ncu) refuse cooperative cluster launches, so under a profiler - and with

@@ -10,7 +10,11 @@ struct Hp4Plan {
     int RC, NCH, S;                 // rows per W chunk (power of two), chunks per strip, slots of the W ring
     size_t w_st, g_st, n_st, r_st;  // stage strides in bytes (multiples of 128)
     size_t total;                   // dynamic shared memory per CTA
+    size_t log_off;                 // developer instantiation: byte offset of the event log (0 = none), see HP_STAMP4
+    int win0;                       // first strip (iteration) of the logged window
 };
+#define HP4_LOG_STRIPS 32
+#define HP4_LOG_BYTES (HP4_LOG_STRIPS * 16 * 4)
 
 struct HpSweepArgs;
 int hp_sweep4_plan(const HpLayout& L, int b, size_t max_smem, Hp4Plan& pl, int RT = 1);   // RT right-hand sides per launch

@@ -32,5 +32,5 @@ for R in Rs:
     for i, nm in enumerate(names):
         if nm != "-":
             print(f"   {nm:16s} {out[:, i].mean() / nst:9.0f} {out[:, i].min() / nst:9.0f} {out[:, i].max() / nst:9.0f}")
-    np.save(f"gpurun_out/multi_phase_R{R}.npy", out)
+    np.save(f"gpurun_out/multi_phase_R{R}{os.environ.get('TAG', '')}.npy", out)
     print("   sums: critical %.0f  off-path %.0f" % (out[:, :6].sum(1).mean() / nst, out[:, 8:15].sum(1).mean() / nst), flush=True)
