@@ -25,9 +25,6 @@
 #define HP4D_NPOLL 3        // off-path warps 4..6 fetch the gf partials of the right neighbour after their interface products
 #define HP4D_PW 4          // words per lane and round of the poll warp
 #define HP4D_EW 3          // gathered entries per warp and batch
-#ifndef HP4D_GATE
-#define HP4D_GATE 1        // the correction of the off-path group waits for the rows of the critical group (see below)
-#endif
 
 struct Hp4dPlan {
     int RC, NCH, S;                     // rows per W chunk, chunks per strip (all resident at once), slots of the W ring
@@ -126,8 +123,7 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
     unsigned long long* eR = eN + 2;                 // [2]
     unsigned long long* barGF = eR + 2;              // [2]
     unsigned long long* eGF = barGF + 2;             // [2]
-    unsigned long long* barC = eGF + 2;              // [2]  the critical group has published its rows of strip it (gates the correction)
-    volatile unsigned int* dead = reinterpret_cast<volatile unsigned int*>(barC + 2);
+    volatile unsigned int* dead = reinterpret_cast<volatile unsigned int*>(eGF + 2);
 
     const cplx* pk_base = a.packets + (size_t)g_ * a.lay.PK;
     const size_t strip_stride = (size_t)a.lay.G * a.lay.PK;
@@ -139,7 +135,7 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
         for (int i = 0; i < S + 13; ++i) mbar_init(&mbar[i], 1);
         for (int i = 0; i < S + 3; ++i) mbar_init(&eW[i], HP4_OFF / 32);
         for (int i = 0; i < 4; ++i) mbar_init(&eN[i], HP4_CW);
-        for (int i = 0; i < 2; ++i) { mbar_init(&barGF[i], HP4D_NPOLL); mbar_init(&eGF[i], HP4_CW); mbar_init(&barC[i], HP4_CW); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&barGF[i], HP4D_NPOLL); mbar_init(&eGF[i], HP4_CW); }
         *dead = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
@@ -331,7 +327,7 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
                 }
                 HPD_TICK(3);
                 __syncwarp();
-                if (lane == 0) { mbar_arrive_local(&barC[par]); mbar_arrive_local(&eN[par]); mbar_arrive_local(&eR[par]); }
+                if (lane == 0) { mbar_arrive_local(&eN[par]); mbar_arrive_local(&eR[par]); }
                 if (ctid == 0 && it + 2 < nsteps) mbar_expect_tx(&barGL[par], gl_bytes);
             }
             // ---- D: gather x3(it): a warp load covers 4 separators x 8 right-hand sides of one entry
@@ -589,12 +585,6 @@ __global__ void __launch_bounds__(HP4D_THREADS, 1) hp_sweep4d_kernel(HpSweepArgs
                     cfrag_zero4(cr);
                     if (any_sep) {
                         mbar_wait4(&barX[par ^ 1], ((it - 1) >> 1) & 1, abort_flag, dead);
-                        // The critical warps form rho(it) and their rows of x(it) from the same x3(it-1) right now.  Their
-                        // tile products are short dependent DMMA chains; next to the 8 off-path warps (12 independent
-                        // chains each) they got a third of the FP64 pipe and took 7.6k cycles per strip, while this group
-                        // has 9k cycles of slack per strip: the correction (and with it the leaf product) starts when the
-                        // rows are out.
-                        if (HP4D_GATE && has_sep && live) mbar_wait4(&barC[par], ph, abort_flag, dead);
                         HPD_TICK(2);
                         const cplx* xa = x3 + (size_t)(par ^ 1) * RT * B3V;
                         for (int ks0 = 0; ks0 < nks_x; ks0 += NST) {
@@ -720,7 +710,7 @@ static int hp_sweep4d_plan(const HpLayout& L, int b, size_t max_smem, Hp4dPlan& 
     pl.n_st = al128d(std::max<size_t>(1, (size_t)b * pl.NRQV) * sizeof(cplx));
     pl.r_st = al128d((size_t)b * 3 * b * sizeof(cplx));
     size_t small = sizeof(cplx) * ((size_t)RT * pl.CWV + 2 * (size_t)RT * pl.QPV + 2 * (size_t)RT * pl.CWV + 2 * (size_t)RT * pl.B3V +
-                                   2 * (size_t)L.K * b * RT + 2 * (size_t)b * RT + 3 * (size_t)RT * pl.BV) + 8 * (2 * 8 + 13 + 7 + 4 + 2) + 16;
+                                   2 * (size_t)L.K * b * RT + 2 * (size_t)b * RT + 3 * (size_t)RT * pl.BV) + 8 * (2 * 8 + 13 + 7 + 4) + 16;
     size_t fixed = 3 * pl.g_st + 2 * pl.n_st + 2 * pl.r_st + al128d(small);
     if (fixed + 1024 >= max_smem) return 1;
     size_t avail = max_smem - 1024 - fixed;

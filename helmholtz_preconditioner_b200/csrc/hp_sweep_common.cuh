@@ -32,6 +32,13 @@ __device__ __forceinline__ cplx ldcg(const cplx* p) {
     double2 v = __ldcg(reinterpret_cast<const double2*>(p));
     return v;
 }
+// the same load pinned where it is written: the compiler may sink a plain load down to its first use, i.e. behind the
+// mbarrier waits of the strip (the point of an early load is that its DRAM latency passes during those waits)
+__device__ __forceinline__ cplx ldcg_now(const cplx* p) {
+    cplx v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
 
 // ---- self-validating exchange words -----------------------------------------------------------------
 #define HP_SENTINEL 0xFFFFFFFFFFFFFFFFull

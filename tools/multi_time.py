@@ -13,7 +13,7 @@ print("layout", {k: s.layout()[k] for k in ("P", "K", "CW", "QP", "NRQ", "NXG")}
 g = torch.Generator(device="cuda").manual_seed(1)
 xs = [torch.randn(n * n, dtype=torch.complex128, device="cuda", generator=g) for _ in range(8)]
 ref = [s.precond_apply(x) for x in xs]
-for R in (1, 2, 4, 8):
+for R in [int(x) for x in os.environ.get("RS", "1,2,4,8").split(",")]:
     if R > s.multi_max:
         break
     outs = [torch.empty_like(x) for x in xs[:R]]
