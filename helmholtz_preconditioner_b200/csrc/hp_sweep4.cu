@@ -34,6 +34,12 @@
 
 // MODE: 0 forward, 1 backward (reference diagonal), 2 backward (paper diagonal), 3 single strip apply
 // BT, KT: PML width and cluster size as compile-time constants (0 = run-time values)
+// partial solutions in the exchange slot: word (entry e, producer cluster p)
+#ifdef HP4_XS_PMAJOR
+#define HP4_XS_IDX(e, p) ((size_t)(p) * NS + (e))          // producer-major: coalesced stores, gathered polls
+#else
+#define HP4_XS_IDX(e, p) ((size_t)(e) * PP + (p))          // entry-major: scattered stores, one coalesced poll per entry
+#endif
 template <int MODE, bool DBG, int BT, int KT>
 __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a, Hp4Plan pl) {
     constexpr int a_mode = MODE == 0 ? 0 : (MODE == 3 ? 2 : 1);
@@ -254,8 +260,8 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
                         a3 = cfma(Np[(size_t)(c + 3) * NRQ + r], rho_s[c + 3], a3);
                     }
                     for (; c < b; ++c) a0 = cfma(Np[(size_t)c * NRQ + r], rho_s[c], a0);
-                    xput(slot + a.oXS + (size_t)(NRQ * k + r) * PP + l, cadd(cadd(a0, a1), cadd(a2, a3)));
-                    xarm(slot_next + a.oXS + (size_t)(NRQ * k + r) * PP + l);
+                    xput(slot + a.oXS + HP4_XS_IDX(NRQ * k + r, l), cadd(cadd(a0, a1), cadd(a2, a3)));
+                    xarm(slot_next + a.oXS + HP4_XS_IDX(NRQ * k + r, l));
                 }
                 HP_TICK(3);
                 HP_STAMP4(4);
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(HP4_THREADS, 1) hp_sweep4_kernel(HpSweepArgs a
 #pragma unroll
                             for (int pp = 0; pp < HP4_PL; ++pp) {
                                 lo[o][pp] = hi[o][pp] = 0ull;
-                                if (ent[o] >= 0 && lane + 32 * pp < P - 1) xload(slot + a.oXS + (size_t)ent[o] * PP + lane + 32 * pp, lo[o][pp], hi[o][pp]);
+                                if (ent[o] >= 0 && lane + 32 * pp < P - 1) xload(slot + a.oXS + HP4_XS_IDX(ent[o], lane + 32 * pp), lo[o][pp], hi[o][pp]);
                             }
                         bool ok = true;
 #pragma unroll
