@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tts", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="N > 1: skip slab_parity and the single-right-hand-side BASELINE configs")
+    ap.add_argument("--mp-schedule", default="lockstep", choices=["async", "lockstep"],
+                    help="N > 1, pipelined mode: groups of right-hand sides as independent pipelines (slab.GroupPipeline) or all in lock step")
     ap.add_argument("--mp-mode", default="pipelined", choices=["pipelined", "weak"],
                     help="N > 1: 'pipelined' (default) = the 4096^2 problem slab-decomposed, --rhs right-hand sides per GPU sent through "
                          "the slabs one behind the other; 'weak' = only the single-right-hand-side weak-scaling case (n = 4096 sqrt(N))")
@@ -524,6 +526,24 @@ def slab_parity(torch, dist, hp, args, rank, world, dev):
     dist.all_reduce(ebt, op=dist.ReduceOp.MAX)
     vec = DeviceVectors(xl.numel(), dev, group=dist.group.WORLD)
     fl = torch.from_numpy(f_mat[S.j0:S.j1].ravel().astype(np.complex128)).to(dev)
+    # groups of right-hand sides as independent pipelines (threads, streams, solver contexts, communicators) against the
+    # same systems advanced in lock step
+    from helmholtz_preconditioner_b200.slab import GroupPipeline
+    from helmholtz_preconditioner_b200.gmres import gmres_batch
+    fgs = [torch.from_numpy(np.ascontiguousarray(np.roll(f_mat, 31 * i, axis=1)[S.j0:S.j1].ravel().astype(np.complex128))).to(dev) for i in range(6)]
+    kwg = dict(rtol=1e-3, restart=20, maxiter=6, nglobal=n * n)
+    pipe = GroupPipeline(S, 3)
+    rg = pipe.gmres([fgs[0:2], fgs[2:4], fgs[4:6]], lambda nloc, pg: DeviceVectors(nloc, dev, group=pg), diag="paper", **kwg)
+    torch.cuda.synchronize()
+    st_pipe = pipe.sweep_status()
+    pipe.close()
+    rl = gmres_batch(lambda a, o: S.matvec(a, o), lambda reqs: S.precond_apply_batch(reqs, diag="paper"), fgs, vec=vec,
+                     matvec_batch=lambda reqs: S.matvec_batch(reqs), **kwg)
+    num = torch.stack([torch.linalg.norm(a[0] - c[0]) ** 2 for a, c in zip([x for grp in rg for x in grp], rl)])
+    den = torch.stack([torch.linalg.norm(c[0]) ** 2 for c in rl])
+    dist.all_reduce(num); dist.all_reduce(den)
+    eg = float(torch.sqrt(num / den).max().item())
+    iters_equal = all(len(a[2]) == len(c[2]) and a[1] == c[1] for a, c in zip([x for grp in rg for x in grp], rl))
     u, info, hist = gmres(lambda a, o: S.matvec(a, o), lambda a, o: S.precond_apply(a, o, diag="paper"), fl, vec=vec,
                           rtol=1e-3, restart=20, maxiter=15, nglobal=n * n)
     res["u"] = u
@@ -548,10 +568,11 @@ def slab_parity(torch, dist, hp, args, rank, world, dev):
         u1, info1, hist1 = gmres(lambda a, o: s1.matvec(a, o), lambda a, o: s1.precond_apply(a, out=o, diag="paper"), f1, vec=v1,
                                  rtol=1e-3, restart=20, maxiter=15)
         out = {"n": n, "M": rel(full["M"], s1.precond_apply(xf)), "A": rel(full["A"], s1.matvec(xf)), "u": rel(full["u"], u1),
-               "gmres_iters": [len(hist), len(hist1)], "batch_vs_one_by_one": ebt.item(), "sweep_status": st,
-               "tolerances": {"M": 1e-11, "A": 1e-13, "u": 1e-8, "batch_vs_one_by_one": 1e-13}}
+               "gmres_iters": [len(hist), len(hist1)], "batch_vs_one_by_one": ebt.item(), "sweep_status": max(st, st_pipe),
+               "groups_vs_lock_step": eg, "groups_iters_equal": bool(iters_equal),
+               "tolerances": {"M": 1e-11, "A": 1e-13, "u": 1e-8, "batch_vs_one_by_one": 1e-13, "groups_vs_lock_step": 1e-10}}
         out["ok"] = bool(out["M"] < 1e-11 and out["A"] < 1e-13 and out["u"] < 1e-8 and len(hist) == len(hist1) and
-                         ebt.item() < 1e-13 and st == 0)
+                         ebt.item() < 1e-13 and st == 0 and st_pipe == 0 and eg < 1e-10 and iters_equal)
         s1.close()
     torch.cuda.empty_cache()
     return out
@@ -646,8 +667,17 @@ def run_b200_slabs(args):
         mvb = lambda reqs: S.matvec_batch(reqs)                   # noqa: E731
         psb = lambda reqs: S.precond_apply_batch(reqs)            # noqa: E731
 
+        pipe = None
+        if args.mp_schedule == "async":
+            from helmholtz_preconditioner_b200.slab import GroupPipeline
+            pipe = GroupPipeline(S, world)                        # one group of args.rhs right-hand sides per GPU
+
         def iterations(k, rhs):
-            return gmres_batch(mv, psb, rhs, vec=vec, matvec_batch=mvb, rtol=0.0, atol=0.0, restart=20, maxiter=k, nglobal=n * n)
+            if pipe is None:
+                return gmres_batch(mv, psb, rhs, vec=vec, matvec_batch=mvb, rtol=0.0, atol=0.0, restart=20, maxiter=k, nglobal=n * n)
+            res = pipe.gmres([rhs[g * args.rhs:(g + 1) * args.rhs] for g in range(world)],
+                             lambda nloc, pg: DeviceVectors(nloc, dev, group=pg), rtol=0.0, atol=0.0, restart=20, maxiter=k, nglobal=n * n)
+            return [x for grp in res for x in grp]
 
         iterations(args.warmup, fs)
         clocks = ClockSampler(local)
@@ -679,10 +709,12 @@ def run_b200_slabs(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         fb = torch.tensor([float(S.s.precond_bytes)], device=dev)
         dist.all_reduce(fb)
-        st = torch.tensor([S.s.sweep_status()], device=dev)
+        st = torch.tensor([max(S.s.sweep_status(), pipe.sweep_status() if pipe is not None else 0)], device=dev)
         dist.all_reduce(st, op=dist.ReduceOp.MAX)
         hist_last = res[0][2][-1] if res[0][2] else None
-        group = S.batch_group(len(fs))
+        group = S.batch_group(args.rhs if pipe is not None else len(fs))
+        if pipe is not None:
+            pipe.close()
         S.s.close()
         del S, res, res2, fs, fs2, vec
         torch.cuda.empty_cache()
@@ -690,7 +722,10 @@ def run_b200_slabs(args):
             clk = clocks.stop()
             total_steps = args.steps * R
             cfg = config_dict(w, world, args.rhs)
-            cfg["parallelism"] = f"slab{world}, {R} right-hand sides ({args.rhs} per GPU) pipelined through the slabs in groups of {group}"
+            cfg["parallelism"] = (f"slab{world}, {R} right-hand sides ({args.rhs} per GPU) pipelined through the slabs in groups of {group}, " +
+                                  ("every group an independent GMRES (own thread, stream, solver context, communicator)" if args.mp_schedule == "async"
+                                   else "all groups in lock step"))
+            cfg["schedule"] = args.mp_schedule
             cfg["rhs_in_flight"] = R
             out = {"metric": METRIC, "value": total_steps / t_dev.item(), "unit": "iters/s",
                    "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev.item() / args.steps,

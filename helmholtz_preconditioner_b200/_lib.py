@@ -22,6 +22,7 @@ SIGNATURES = {
     "hp_profile_read": (_i, [_vp, C.POINTER(_d), _ip, C.POINTER(_i64)]),
     "hp_create": (_i, [C.POINTER(_vp), _i, _i, _d, _d, _d, _vp, _i, _vp]),
     "hp_destroy": (_i, [_vp]),
+    "hp_context_clone": (_i, [_vp, C.POINTER(_vp), _vp]),
     "hp_csr_nnz": (_i64, [_i]),
     "hp_assemble_csr": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hp_strip_csr_nnz": (_i64, [_i, _i]),

@@ -105,8 +105,39 @@ extern "C" int hp_create(hp_solver** out, int n, int b, double omega_re, double 
     return 0;
 }
 
+// A second handle on the same operator and factorisation with its own sweep scratch (exchange ring, abort flags, parked
+// front solutions): sweeps issued through different contexts may be in flight on different streams at the same time
+// (slab.py: the groups of right-hand sides of the asynchronous pipeline).  Everything read-only is shared with `s`, which
+// must outlive the context; hp_destroy on a context frees its scratch only.
+extern "C" int hp_context_clone(hp_solver* s, hp_solver** out, void* stream) {
+    if (!s || !out) { hp_set_error("hp_context_clone: null argument"); return 1; }
+    *out = nullptr;
+    if (!s->f_low || !s->bar) { hp_set_error("hp_context_clone: preconditioner not set up"); return 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    hp_solver* c = new hp_solver(*s);
+    c->is_view = 1;
+    c->xch = nullptr; c->bar = nullptr; c->TF = nullptr; c->TFm = nullptr; c->fc_work = nullptr; c->dbg = nullptr;
+    c->prof_on = 0; c->prof_ev.clear(); c->prof_used = 0; c->prof_bytes = 0;
+    auto fail = [&]() { hp_destroy(c); return 2; };
+    const size_t sz = sizeof(cplx) * (size_t)s->b * s->n;
+    if (cudaMalloc(&c->xch, sizeof(cplx) * s->xch_count) != cudaSuccess || cudaMalloc(&c->bar, sizeof(unsigned int) * s->bar_count) != cudaSuccess ||
+        cudaMalloc(&c->TF, 2 * sz) != cudaSuccess || (s->fc_work && cudaMalloc(&c->fc_work, sz) != cudaSuccess) ||
+        cudaMemsetAsync(c->bar, 0, sizeof(unsigned int) * s->bar_count, st) != cudaSuccess) {
+        hp_set_error("hp_context_clone: allocation of the sweep scratch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail();
+    }
+    *out = c;
+    return 0;
+}
+
 extern "C" int hp_destroy(hp_solver* s) {
     if (!s) return 0;
+    if (s->is_view) {
+        cudaFree(s->xch); cudaFree(s->bar); cudaFree(s->TF); cudaFree(s->TFm); cudaFree(s->fc_work); cudaFree(s->dbg);
+        for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
+        delete s;
+        return 0;
+    }
     hp_free_strips(s);
     cudaFree(s->s1t); cudaFree(s->is1t); cudaFree(s->s2t); cudaFree(s->is2t);
     cudaFree(s->c_mat); cudaFree(s->kappa); cudaFree(s->status);
@@ -119,6 +150,7 @@ extern "C" int hp_destroy(hp_solver* s) {
 
 extern "C" int hp_precond_setup(hp_solver* s, int P, int K, int m_lo, int m_hi, void* stream) {
     if (!s) { hp_set_error("hp_precond_setup: null solver"); return 1; }
+    if (s->is_view) { hp_set_error("hp_precond_setup: a context made by hp_context_clone shares the factorisation of its parent"); return 1; }
     if (m_lo == 0 && m_hi == 0) { m_lo = s->b + 1; m_hi = s->n; }
     if (m_lo < s->b + 1 || m_hi > s->n) {
         hp_set_error("hp_precond_setup: strips must lie in %d..%d, got %d..%d", s->b + 1, s->n, m_lo, m_hi);
@@ -159,6 +191,7 @@ extern "C" int hp_set_front_mode(hp_solver* s, int mode) {
 }
 // re-factor the front block alone with another mode; the strip factorisation is kept
 extern "C" int hp_precond_set_front(hp_solver* s, int mode, void* stream) {
+    if (s && s->is_view) { hp_set_error("hp_precond_set_front: not on a context made by hp_context_clone"); return 1; }
     if (hp_set_front_mode(s, mode)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     HP_CUDA(cudaMemsetAsync(s->status, 0, sizeof(int), st));

@@ -1268,9 +1268,11 @@ int hp_setup_strips(hp_solver* s, int P_req, int K_req, int m_lo, int m_hi, cuda
     tr.mark("packets cleared", st, true);
     size_t xch_classic = (size_t)n + (size_t)L.G * 2 * b + (size_t)L.P * 2 * b + L.NSP + L.P;
     size_t xch_cluster = ((size_t)L.G * b + (size_t)std::max(L.NS, 1) * (L.P | 1)) * 8;   // x HP_RMAX right-hand sides per launch
-    HP_CUDA(cudaMalloc(&s->xch, sizeof(cplx) * 4 * std::max(xch_classic, xch_cluster)));
-    HP_CUDA(cudaMalloc(&s->bar, sizeof(unsigned int) * (4 + L.P)));
-    HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int) * (4 + L.P), st));
+    s->xch_count = 4 * std::max(xch_classic, xch_cluster);
+    s->bar_count = (size_t)(4 + L.P);
+    HP_CUDA(cudaMalloc(&s->xch, sizeof(cplx) * s->xch_count));
+    HP_CUDA(cudaMalloc(&s->bar, sizeof(unsigned int) * s->bar_count));
+    HP_CUDA(cudaMemsetAsync(s->bar, 0, sizeof(unsigned int) * s->bar_count, st));
     s->m_lo = m_lo; s->m_hi = m_hi;
     s->bytes = (int64_t)pbytes;
 

@@ -246,3 +246,103 @@ def distributed_gmres_setup(n, b, omega, const, c_mat, rank, world, group, devic
     m_lo, m_hi = max(b + 1, R[rank] + 1), min(n, R[rank + 1])
     s.setup_preconditioner(P, K, m_lo, m_hi)
     return SlabSolver(s, n, b, rank, world, group, device=device, front_equiv=front_equiv)
+
+
+class GroupPipeline:
+    """Groups of right-hand sides that run through the slabs independently of each other.
+
+    precond_apply_batch/gmres_batch advance all right-hand sides in lock step: every sweep direction of every Krylov
+    iteration fills and drains the chain of slabs, G groups take (world - 1 + G) slab sweeps per direction and a rank is
+    busy G / (world - 1 + G) of the time.  Here every group of right-hand sides (one launch of the multi-vector sweep
+    kernel per slab and direction) is an independent restarted GMRES with its own
+      * host thread (runs gmres_batch on the systems of the group and blocks on its own results only),
+      * CUDA stream (the device takes the next ready kernel of any group: a greedy list schedule of the slab sweeps),
+      * solver context (HelmholtzSolver.clone_context: private exchange ring / abort flags / parked front solutions),
+      * process group (its own communicator, so that no order of calls has to be kept between the groups).
+    A group starts its next iteration as soon as its own backward sweep has reached rank 0, while the other groups are
+    anywhere in their sweeps: in the steady state a rank always has a slab sweep or the vector work of some group to
+    run as soon as there are about as many groups as ranks.  The arithmetic of a system is that of gmres_batch on its
+    group alone: results do not depend on how the groups interleave.
+
+    Device-side progress: a group has at most one communication kernel in flight, and the NCCL communicators of the groups
+    are limited to one CTA per kernel (pg_options below), so the at most G waiting communication kernels occupy G SMs
+    while a sweep kernel needs P * K of them to be free at once (132 of 148 at 4096^2): with G <= 8 a sweep can always start.
+    """
+
+    def __init__(self, S, n_groups, device=None, backend="nccl", streams=True):
+        self.S, self.G = S, int(n_groups)
+        self.device = S.device if device is None else device
+        self.cuda = torch.device(self.device).type == "cuda"
+        self.members = []
+        for g in range(self.G):
+            pg = None
+            if S.world > 1:
+                opts = None
+                if backend == "nccl":
+                    opts = dist.ProcessGroupNCCL.Options()
+                    opts.config.min_ctas = 1
+                    opts.config.max_ctas = 1
+                pg = dist.new_group(backend=backend, pg_options=opts) if opts is not None else dist.new_group(backend=backend)
+            ctx = S.s.clone_context() if hasattr(S.s, "clone_context") else S.s
+            Sg = SlabSolver(ctx, S.n, S.b, S.rank, S.world, pg, device=self.device)
+            Sg.R, Sg.j0, Sg.j1, Sg.rows, Sg.m_lo, Sg.m_hi = S.R, S.j0, S.j1, S.rows, S.m_lo, S.m_hi
+            stream = torch.cuda.Stream(device=self.device) if (self.cuda and streams) else None
+            self.members.append((Sg, pg, stream))
+
+    def close(self):
+        for Sg, pg, _ in self.members:
+            if Sg.s is not self.S.s and hasattr(Sg.s, "close"):
+                Sg.s.close()
+            if pg is not None:
+                dist.destroy_process_group(pg)
+        self.members = []
+
+    def sweep_status(self):
+        return max([int(Sg.s.sweep_status()) for Sg, _, _ in self.members if hasattr(Sg.s, "sweep_status")] + [0])
+
+    def gmres(self, rhs_groups, make_vec, *, diag="reference", **kw):
+        """rhs_groups[g]: list of local right-hand side slabs of group g; make_vec(nloc, process_group) -> the vector
+        kernels of a group (gmres.DeviceVectors on a GPU).  Returns [[(x, info, hist), ...] per group]."""
+        import contextlib
+        import sys
+        import threading
+        from .gmres import gmres_batch
+        assert len(rhs_groups) == self.G
+        results, errors = [None] * self.G, [None] * self.G
+        start = torch.cuda.Event() if self.cuda else None
+        if start is not None:
+            start.record()                                   # the groups start after what the caller has enqueued
+
+        def work(g):
+            Sg, pg, stream = self.members[g]
+            try:
+                with (torch.cuda.device(self.device) if self.cuda else contextlib.nullcontext()):
+                    with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+                        if stream is not None:
+                            stream.wait_event(start)
+                        vec = make_vec(rhs_groups[g][0].numel(), pg)
+                        results[g] = gmres_batch(lambda x, o: Sg.matvec(x, o), lambda reqs: Sg.precond_apply_batch(reqs, diag=diag),
+                                                 rhs_groups[g], vec=vec, matvec_batch=lambda reqs: Sg.matvec_batch(reqs), **kw)
+                        if stream is not None:
+                            stream.synchronize()
+            except BaseException as e:                       # noqa: B902 - reported by the caller's thread
+                errors[g] = e
+
+        old = sys.getswitchinterval()
+        sys.setswitchinterval(1e-4)                          # a thread whose result has arrived should not wait 5 ms for the GIL
+        try:
+            threads = [threading.Thread(target=work, args=(g,), name=f"hp-group-{g}") for g in range(self.G)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+        finally:
+            sys.setswitchinterval(old)
+        for e in errors:
+            if e is not None:
+                raise e
+        if self.cuda:
+            for _, _, stream in self.members:
+                if stream is not None:
+                    torch.cuda.current_stream().wait_stream(stream)
+        return results

@@ -73,6 +73,20 @@ class HelmholtzSolver:
         self.m_lo, self.m_hi = 0, -1
         self.max_group = 8            # cap on the right-hand sides per sweep launch (1 = one launch per vector)
 
+    def clone_context(self):
+        """A second handle on this solver's operator and factorisation with private sweep scratch (hp_context_clone):
+        preconditioner applications issued through different contexts may be in flight on different CUDA streams at the
+        same time (one context per group of right-hand sides in slab.GroupPipeline).  Close the contexts before the
+        solver they were cloned from."""
+        self._on_device()
+        c = object.__new__(HelmholtzSolver)
+        c.__dict__.update(self.__dict__)
+        h = C.c_void_p()
+        _lib.check(self.lib.hp_context_clone(self.handle, C.byref(h), _stream()), "hp_context_clone")
+        c.handle = h
+        c.parent = self                                      # keeps the owner of the factorisation alive
+        return c
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.hp_destroy(self.handle)

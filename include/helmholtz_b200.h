@@ -40,6 +40,12 @@ int hp_profile_read(hp_solver* s, double* sweep_ms, int* launches, int64_t* byte
 int hp_create(hp_solver** out, int n, int b, double omega_re, double omega_im, double cst,
               const double* c_mat, int c_is_device, void* stream);
 int hp_destroy(hp_solver* s);
+/* A second handle on a solver that is set up: shares the operator tables and the factorisation (read-only) and owns a
+ * private copy of the sweep scratch (exchange ring, abort flags, parked front solutions T_F u_F of code.py:364), so that
+ * applications of algo2_4 (code.py:356-385) issued through different contexts can be in flight on different streams at
+ * once.  The reference has no counterpart (one Python thread); slab.py uses one context per group of right-hand sides.
+ * `s` must outlive the context; hp_destroy(context) frees the scratch only; setup calls on a context are refused. */
+int hp_context_clone(hp_solver* s, hp_solver** out, void* stream);
 
 /* ---- operator A ---------------------------------------------------------------------------------- */
 

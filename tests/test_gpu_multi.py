@@ -74,3 +74,37 @@ def test_multi_vs_oracle(hp):
             assert np.linalg.norm(o.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-12
     s.check_status()
     s.close()
+
+
+@pytest.mark.parametrize("front", ["blockdiag", "coupled"])
+def test_group_pipeline_one_gpu(hp, front):
+    """slab.GroupPipeline on one GPU (world 1): three groups of right-hand sides, each with its own thread, stream and solver
+    context (hp_context_clone), their sweeps interleaving on the device, must give bit for bit what the lock-step batch
+    on the parent solver gives, and the contexts must not disturb each other (exchange ring, parked front solutions)."""
+    from helmholtz_preconditioner_b200.slab import SlabSolver, GroupPipeline
+    from helmholtz_preconditioner_b200.gmres import DeviceVectors, gmres_batch
+    n, b = 1024, 12
+    omega = 2 * np.pi * (n / 10) + 2j
+    c_mat, f_mat = hp.init_layered_f1(omega, n)
+    s = hp.HelmholtzSolver(n, b, omega, 100.0, c_mat).setup_preconditioner(front=front)
+    S = SlabSolver(s, n, b, 0, 1, None, device=s.device)
+    sizes = [8, 8, 3]
+    fs = [torch.from_numpy(np.roll(f_mat, 17 * i, axis=1).ravel().astype(np.complex128)).cuda() for i in range(sum(sizes))]
+    groups, i = [], 0
+    for g in sizes:
+        groups.append(fs[i:i + g]); i += g
+    kw = dict(rtol=1e-3, restart=20, maxiter=7, nglobal=n * n)
+    pipe = GroupPipeline(S, len(sizes))
+    res = pipe.gmres(groups, lambda nloc, pg: DeviceVectors(nloc, s.device, group=pg), diag="paper", **kw)
+    torch.cuda.synchronize()
+    assert pipe.sweep_status() == 0
+    pipe.close()
+    for grp, rg in zip(groups, res):
+        vec = DeviceVectors(n * n, s.device)
+        lock = gmres_batch(lambda x, o: S.matvec(x, o), lambda reqs: S.precond_apply_batch(reqs, diag="paper"), grp, vec=vec,
+                           matvec_batch=lambda reqs: S.matvec_batch(reqs), **kw)
+        for (u, info, hist), (u0, info0, hist0) in zip(rg, lock):
+            assert info == info0 and hist == hist0
+            assert torch.equal(u, u0)
+    s.check_status()
+    s.close()

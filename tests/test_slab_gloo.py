@@ -39,6 +39,10 @@ class NumpyBackend:
         Au[-n:] = self.P.up[b - 1] * u[b - r0]
         u[0 - r0:b - r0] = (self.TF - self.P.lu_HF.solve(Au)).reshape(b, n)
 
+    def clone_context(self):
+        import copy
+        return copy.copy(self)                               # shares the factorisation, own parked front solution (self.TF)
+
     def front_tf_new(self):
         return [None]
 
@@ -156,15 +160,16 @@ def test_slab_bounds():
 class NumpyVectors:
     """DeviceVectors (helmholtz_preconditioner_b200/gmres.py) on CPU tensors: same interface, reductions over gloo."""
 
-    def __init__(self):
+    def __init__(self, group=None):
         self.allreduces = 0
+        self.group = group
 
     def reserve(self, restart):
         pass
 
     def _sum(self, arr):
         t = torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=np.complex128)))
-        dist.all_reduce(torch.view_as_real(t))
+        dist.all_reduce(torch.view_as_real(t), group=self.group)
         self.allreduces += 1
         return t.numpy()
 
@@ -247,3 +252,42 @@ def test_distributed_gmres_batch_matches_oracle(world):
             assert np.allclose(hist, hist0, rtol=1e-8)
             assert np.linalg.norm(u - u0) / np.linalg.norm(u0) < 1e-8
     assert ret[0]["n_batch"] * 3 == ret[0]["n_one"]
+
+
+# ---- groups of right-hand sides as independent pipelines (slab.GroupPipeline): threads, one process group per group ---
+def _group_worker(rank, world, port, n, b, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from helmholtz_preconditioner_b200.slab import SlabSolver, GroupPipeline
+    from helmholtz_preconditioner_b200.gmres import gmres_batch
+    omega = 2 * np.pi * 4 + 2j
+    c_mat, f_mat = orc.init_c1_f1(omega, n)
+    be = NumpyBackend(n, b, omega, 61.0, c_mat)
+    S = SlabSolver(be, n, b, rank, world)
+    fs = [np.roll(f_mat, s, axis=1) for s in (0, 7, -5, 3, -9, 11)]
+    loc = [torch.from_numpy(np.ascontiguousarray(f[S.j0:S.j1].ravel().astype(np.complex128))) for f in fs]
+    kw = dict(rtol=1e-3, restart=20, maxiter=9, nglobal=n * n)
+    pipe = GroupPipeline(S, 3, device="cpu", backend="gloo")
+    res = pipe.gmres([loc[0:2], loc[2:4], loc[4:6]], lambda nloc, pg: NumpyVectors(pg), **kw)
+    pipe.close()
+    vec = NumpyVectors()
+    lock = gmres_batch(lambda x, o: S.matvec(x, o), lambda reqs: S.precond_apply_batch(reqs), loc, vec=vec,
+                       matvec_batch=lambda reqs: S.matvec_batch(reqs), **kw)
+    flat = [r for grp in res for r in grp]
+    ret[rank] = dict(pipe=[(u.numpy().copy(), info, hist) for u, info, hist in flat],
+                     lock=[(u.numpy().copy(), info, hist) for u, info, hist in lock])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_group_pipeline_matches_lock_step(world):
+    """independent groups (threads, own process groups) give what the lock-step batch gives (to rounding: the all-reduce of
+    another process group may sum the ranks in another order)"""
+    n, b = 40, 5
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_group_worker, args=(world, _free_port(), n, b, ret), nprocs=world, join=True)
+    for r in range(world):
+        for (u, info, hist), (u0, info0, hist0) in zip(ret[r]["pipe"], ret[r]["lock"]):
+            assert info == info0 and len(hist) == len(hist0) and np.allclose(hist, hist0, rtol=1e-10)
+            assert np.linalg.norm(u - u0) / np.linalg.norm(u0) < 1e-10
