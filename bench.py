@@ -631,6 +631,12 @@ def slab_single_rhs(torch, dist, hp, args, n, rank, world, dev, steps=5, warmup=
 
 
 def run_b200_slabs(args):
+    # before CUDA starts: (i) eager module loading - the first launch of a lazily loaded kernel may synchronise the whole
+    # context, a deadlock once streams of this process wait for other GPUs (slab.GroupPipeline primes its groups as well);
+    # (ii) one hardware queue per stream: a stream that waits for a sequence number of a neighbour (csrc/hp_peer.cu) must not
+    # hold back another stream that happens to share its queue (default: 8 queues)
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import torch
     import torch.distributed as dist
     import helmholtz_preconditioner_b200 as hp

@@ -23,6 +23,14 @@ SIGNATURES = {
     "hp_create": (_i, [C.POINTER(_vp), _i, _i, _d, _d, _d, _vp, _i, _vp]),
     "hp_destroy": (_i, [_vp]),
     "hp_context_clone": (_i, [_vp, C.POINTER(_vp), _vp]),
+    "hp_mailbox_create": (_i, [_i64, C.POINTER(_vp), _vp]),
+    "hp_mailbox_open": (_i, [_vp, C.POINTER(_vp)]),
+    "hp_mailbox_close": (_i, [_vp]),
+    "hp_mailbox_free": (_i, [_vp]),
+    "hp_stream_wait_geq": (_i, [_vp, C.c_uint, _vp]),
+    "hp_handover_rows": (_i, [_i, C.POINTER(_vp), _vp, _i64, _vp, C.c_uint, _vp]),
+    "hp_collect_rows": (_i, [_i, _vp, C.POINTER(_vp), _i64, _vp]),
+    "hp_signal_flags": (_i, [_i, C.POINTER(_vp), C.c_uint, _vp]),
     "hp_csr_nnz": (_i64, [_i]),
     "hp_assemble_csr": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hp_strip_csr_nnz": (_i64, [_i, _i]),

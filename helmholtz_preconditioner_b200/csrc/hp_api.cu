@@ -116,6 +116,13 @@ extern "C" int hp_context_clone(hp_solver* s, hp_solver** out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     hp_solver* c = new hp_solver(*s);
     c->is_view = 1;
+    // Sweeps of a context are plain cluster launches.  A cooperative launch is ordered against all other work of the process
+    // on the device (measured: with the sweep of one group queued behind a stream-level wait for another GPU, the cooperative
+    // launch of the next group blocks its host thread inside the launch call, and two processes then wait for each other).
+    // What the cooperative attribute checks, that all P clusters fit on the device at once, was checked when the layout was
+    // chosen (hp_sweep4_max_clusters / cudaOccupancyMaxActiveClusters); a sweep whose clusters are not all resident yet waits
+    // for the SMs that the short kernels of other streams hold.
+    c->coop = 0;
     c->xch = nullptr; c->bar = nullptr; c->TF = nullptr; c->TFm = nullptr; c->fc_work = nullptr; c->dbg = nullptr;
     c->prof_on = 0; c->prof_ev.clear(); c->prof_used = 0; c->prof_bytes = 0;
     auto fail = [&]() { hp_destroy(c); return 2; };

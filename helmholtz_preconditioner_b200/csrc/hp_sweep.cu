@@ -419,7 +419,8 @@ int hp_sweep_launch(hp_solver* s, int mode, cplx* u, const cplx* vin, cplx* yout
         const void* fn = tma ? (const void*)hp_sweep_kernel<true> : (const void*)hp_sweep_kernel<false>;
         if (smem > 48 * 1024) HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         void* args[] = {&a};
-        HP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.G), dim3(HP_SWEEP_THREADS), args, smem, st));
+        if (s->coop) HP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.G), dim3(HP_SWEEP_THREADS), args, smem, st));
+        else HP_CUDA(cudaLaunchKernel(fn, dim3(L.G), dim3(HP_SWEEP_THREADS), args, smem, st));   // contexts: see hp_context_clone
     }
     hp_profile_end(s, st, (int64_t)(hi - lo + 1) * ((int64_t)L.G * L.PK + 3 * (int64_t)s->n + (L.colN ? (int64_t)(L.P - 1) * 3 * s->b * s->b : 0)) *
                               (int64_t)sizeof(cplx));

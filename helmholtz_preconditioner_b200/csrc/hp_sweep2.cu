@@ -491,6 +491,7 @@ int hp_sweep2_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st) {
     const void* fn = fns[a.dbg ? 1 : 0][mode];
     HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {&a};
-    HP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.G), dim3(HP2_THREADS), args, smem, st));
+    if (s->coop) HP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.G), dim3(HP2_THREADS), args, smem, st));
+    else HP_CUDA(cudaLaunchKernel(fn, dim3(L.G), dim3(HP2_THREADS), args, smem, st));   // contexts: see hp_context_clone
     return 0;
 }

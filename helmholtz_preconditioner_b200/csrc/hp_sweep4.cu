@@ -766,7 +766,7 @@ int hp_sweep4_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st) {
     // and mbarriers).  Kernel-replaying profilers (ncu) refuse cooperative cluster launches, so under a profiler - and with
     // HP_NO_COOP - the plain cluster launch is taken up front: co-residency was checked against
     // cudaOccupancyMaxActiveClusters when the partition was chosen.  Any other failure is an error.
-    if (hp_profiler_attached() || getenv("HP_NO_COOP")) cfg.numAttrs = 1;
+    if (hp_profiler_attached() || getenv("HP_NO_COOP") || !s->coop) cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e != cudaSuccess) {
         cudaGetLastError();

@@ -782,7 +782,7 @@ int hp_sweep4d_launch(hp_solver* s, HpSweepArgs& a, cudaStream_t st) {
     at[1].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 2;
     void* args[] = {&a, &pl};
-    if (hp_profiler_attached() || getenv("HP_NO_COOP")) cfg.numAttrs = 1;      // see hp_sweep4_launch
+    if (hp_profiler_attached() || getenv("HP_NO_COOP") || !s->coop) cfg.numAttrs = 1;      // see hp_sweep4_launch
     cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e != cudaSuccess) {
         cudaGetLastError();

@@ -19,6 +19,9 @@ import torch
 from . import _lib
 
 
+_TRACE = bool(__import__("os").environ.get("HP_GMRES_TRACE"))     # developer switch: one line per served round of gmres_batch
+
+
 def _ptr(t):
     return t.data_ptr()
 
@@ -205,6 +208,10 @@ def gmres_batch(matvec, psolve_batch, bs, *, vec, matvec_batch=None, **kw):
             by_kind.setdefault(key, []).append(i)
         key, idx = next(iter(by_kind.items()))              # lock step: normally a single kind per round
         kind = key if isinstance(key, str) else key[0]
+        if _TRACE:
+            import sys
+            import threading
+            print(f"[gmres_batch {threading.current_thread().name}] {key} x{len(idx)}", file=sys.stderr, flush=True)
         if kind == "M":
             psolve_batch([(reqs[i][1], reqs[i][2]) for i in idx])
             vals = [None] * len(idx)

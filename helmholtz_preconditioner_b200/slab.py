@@ -59,6 +59,7 @@ class SlabSolver:
         self.south = torch.zeros(n, dtype=torch.complex128, device=device)
         self.north = torch.zeros(n, dtype=torch.complex128, device=device)
         self.halos = []                                      # halo rows of a batch of systems (matvec_batch)
+        self.mail, self.seq = None, 0                        # PeerMailbox of this solver (GroupPipeline), applications so far
 
     # -- communication helpers ------------------------------------------------------------------------
     def _send(self, t, dst):
@@ -167,6 +168,8 @@ class SlabSolver:
         the rows handed over are posted as non-blocking sends so that a rank goes on with the next group at once."""
         n, b, r, w = self.n, self.b, self.rank, self.world
         R = len(pairs)
+        if self.mail is not None and w > 1:
+            return self._precond_apply_batch_mailbox(pairs, diag)
         while len(self.bufs) < R:
             self.bufs.append(torch.zeros_like(self.buf))
         if r == 0 and hasattr(self.s, "front_tf_new"):
@@ -238,6 +241,146 @@ class SlabSolver:
             out.copy_(owns[i])
 
 
+    def _precond_apply_batch_mailbox(self, pairs, diag):
+        """precond_apply_batch with the rows handed over through peer mailboxes (PeerMailbox): up to 8 right-hand sides that
+        travel together.  Between the sweeps of this rank and those of its neighbours no communication kernel waits on the
+        device: the stream waits for sequence numbers (application count `seq`) that the neighbour releases after its rows
+        have been stored into this rank's staging area.  Ranks > 0 leave the application only when rank 0 has finished
+        it, so that every collective that follows (halo exchange, dot products) finds all ranks in their vector phase."""
+        n, b, r, w, mail = self.n, self.b, self.rank, self.world, self.mail
+        R = len(pairs)
+        assert R <= mail.R, "a mailbox carries the rows of one group of right-hand sides"
+        self.seq += 1
+        seq = self.seq
+        while len(self.bufs) < R:
+            self.bufs.append(torch.zeros_like(self.buf))
+        if r == 0:
+            while len(self.tfs) < R:
+                self.tfs.append(self.s.front_tf_new())
+        row0 = self.j0 - 1
+        bufs = self.bufs[:R]
+        owns = [bf[n:(self.rows + 1) * n] for bf in bufs]
+        for i, (x, _) in enumerate(pairs):
+            owns[i].copy_(x)
+        ops = []                                             # ghost rows above: initial values of the first row of the next slab
+        for i in range(R):
+            if r > 0:
+                ops.append(dist.P2POp(dist.isend, owns[i][:n], r - 1, self.group))
+            if r < w - 1:
+                ops.append(dist.P2POp(dist.irecv, self._row(self.j1, bufs[i]), r + 1, self.group))
+        self._exchange(ops)
+        groups, i = [], 0
+        while i < R:
+            g = self.batch_group(R - i)
+            groups.append(list(range(i, i + g)))
+            i += g
+        m_to = min(self.m_hi, n - 1)
+        # forward chain
+        if r == 0:
+            for i in range(R):
+                self.s.front_begin_buf(bufs[i], row0)
+                if R > 1:
+                    self.s.front_tf_save(self.tfs[i])
+        else:
+            mail.wait(mail.FWD, seq)
+            mail.collect(mail.FWD, [self._row(self.j0, bf) for bf in bufs])
+        if self.m_lo <= m_to:
+            for grp in groups:
+                if len(grp) > 1:
+                    self.s.sweep_forward_multi_buf([bufs[i] for i in grp], row0, self.m_lo, m_to)
+                else:
+                    self.s.sweep_forward_buf(bufs[grp[0]], row0, self.m_lo, m_to)
+        if r < w - 1:
+            mail.handover(r + 1, mail.FWD, [self._row(self.j1, bf) for bf in bufs], seq)
+            # backward chain
+            mail.wait(mail.BWD, seq)
+            mail.collect(mail.BWD, [self._row(self.j1, bf) for bf in bufs])
+        if self.m_lo <= self.m_hi:
+            for grp in groups:
+                if len(grp) > 1:
+                    self.s.sweep_backward_multi_buf([bufs[i] for i in grp], row0, self.m_hi, self.m_lo, diag)
+                else:
+                    self.s.sweep_backward_buf(bufs[grp[0]], row0, self.m_hi, self.m_lo, diag)
+        if r > 0:
+            mail.handover(r - 1, mail.BWD, [self._row(self.j0, bf) for bf in bufs], seq)
+            mail.wait(mail.DONE, seq)
+        else:
+            for i in range(R):
+                if R > 1:
+                    self.s.front_tf_load(self.tfs[i])
+                self.s.front_end_buf(bufs[i], row0)
+            mail.signal_done(seq)
+        for i, (_, out) in enumerate(pairs):
+            out.copy_(owns[i])
+
+
+class PeerMailbox:
+    """Staging rows and sequence numbers of one group of right-hand sides on this rank, mapped by the neighbouring ranks
+    through CUDA IPC (csrc/hp_peer.cu): [256 bytes of flags | forward staging [R][n] | backward staging [R][n]].
+    Built collectively: create() on every rank, exchange of the handles, connect()."""
+    FWD, BWD, DONE = 0, 1, 2
+
+    def __init__(self, n, R, device):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.require_device()
+        self.C, self.check = C, _lib.check
+        self.n, self.R, self.device = n, R, device
+        self.bytes = 256 + 2 * R * n * 16
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            self.check(self.lib.hp_mailbox_create(self.bytes, C.byref(ptr), handle), "hp_mailbox_create")
+        self.ptr, self.handle = ptr.value, bytes(handle)
+        self.peers = {}                                      # rank -> device address of that rank's mailbox in this process
+
+    def connect(self, handles, rank, world):
+        """handles[r]: the 64-byte handle of rank r's mailbox.  Neighbours map each other; rank 0 maps everybody (DONE)."""
+        C = self.C
+        self.rank, self.world = rank, world
+        need = {rank - 1, rank + 1} if rank > 0 else set(range(1, world))
+        with torch.cuda.device(self.device):
+            for p in sorted(q for q in need if 0 <= q < world and q != rank):
+                ptr = C.c_void_p()
+                h = (C.c_ubyte * 64).from_buffer_copy(handles[p])
+                self.check(self.lib.hp_mailbox_open(h, C.byref(ptr)), "hp_mailbox_open")
+                self.peers[p] = ptr.value
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _staging(self, base, which):
+        return base + 256 + which * self.R * self.n * 16
+
+    def wait(self, which, seq):
+        self.check(self.lib.hp_stream_wait_geq(self.ptr + 4 * which, seq, self._stream()), "hp_stream_wait_geq")
+
+    def collect(self, which, rows):
+        arr = (self.C.c_void_p * len(rows))(*[t.data_ptr() for t in rows])
+        self.check(self.lib.hp_collect_rows(len(rows), self._staging(self.ptr, which), arr, self.n, self._stream()), "hp_collect_rows")
+
+    def handover(self, peer, which, rows, seq):
+        base = self.peers[peer]
+        arr = (self.C.c_void_p * len(rows))(*[t.data_ptr() for t in rows])
+        self.check(self.lib.hp_handover_rows(len(rows), arr, self._staging(base, which), self.n, base + 4 * which, seq, self._stream()),
+                   "hp_handover_rows")
+
+    def signal_done(self, seq):
+        ranks = [p for p in sorted(self.peers) if p > 0]
+        for i in range(0, len(ranks), 8):
+            chunk = ranks[i:i + 8]
+            arr = (self.C.c_void_p * len(chunk))(*[self.peers[p] + 4 * self.DONE for p in chunk])
+            self.check(self.lib.hp_signal_flags(len(chunk), arr, seq, self._stream()), "hp_signal_flags")
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            for p in self.peers.values():
+                self.lib.hp_mailbox_close(p)
+            self.peers = {}
+            if self.ptr:
+                self.lib.hp_mailbox_free(self.ptr)
+                self.ptr = None
+
+
 def distributed_gmres_setup(n, b, omega, const, c_mat, rank, world, group, device, P=0, K=0, front_equiv=0):
     """HelmholtzSolver of this rank with its strips factored, wrapped in a SlabSolver."""
     from .solver import HelmholtzSolver
@@ -264,16 +407,29 @@ class GroupPipeline:
     run as soon as there are about as many groups as ranks.  The arithmetic of a system is that of gmres_batch on its
     group alone: results do not depend on how the groups interleave.
 
-    Device-side progress: a group has at most one communication kernel in flight, and the NCCL communicators of the groups
-    are limited to one CTA per kernel (pg_options below), so the at most G waiting communication kernels occupy G SMs
-    while a sweep kernel needs P * K of them to be free at once (132 of 148 at 4096^2): with G <= 8 a sweep can always start.
+    Device-side progress.  The cluster sweep kernels need every cluster slot of the GPU (33 clusters of 4 whole SMs at
+    4096^2), so a communication kernel that spins on an SM while it waits for a sweep on ANOTHER GPU can keep a sweep of
+    another group partially resident on THIS GPU, and two GPUs can wait for each other that way (measured: the schedule
+    with NCCL receives for the rows hangs at N = 2).  Therefore (i) the rows travel through PeerMailbox: stores into the
+    neighbour's memory and stream-level waits for sequence numbers, no kernel waits for a sweep; (ii) ranks > 0 leave an
+    application of the preconditioner only when rank 0 has finished it, so the NCCL kernels that remain (ghost rows at the
+    start of an application, halo rows of the matvec, dot products; one CTA each, pg_options below) only ever wait for
+    vector kernels of the same group on the other ranks, which always find a free SM.
     """
 
-    def __init__(self, S, n_groups, device=None, backend="nccl", streams=True):
+    def __init__(self, S, n_groups, device=None, backend="nccl", streams=True, rhs_per_group=8, mailboxes=True, solver_cls=None):
         self.S, self.G = S, int(n_groups)
         self.device = S.device if device is None else device
         self.cuda = torch.device(self.device).type == "cuda"
         self.members = []
+        self.mails = []
+        self.primed = False
+        if self.cuda and S.world > 1 and mailboxes:         # row hand-over through peer memory (see PeerMailbox)
+            self.mails = [PeerMailbox(S.n, rhs_per_group, self.device) for _ in range(self.G)]
+            handles = [None] * S.world
+            dist.all_gather_object(handles, [m.handle for m in self.mails])
+            for g, m in enumerate(self.mails):
+                m.connect([handles[r][g] for r in range(S.world)], S.rank, S.world)
         for g in range(self.G):
             pg = None
             if S.world > 1:
@@ -282,14 +438,22 @@ class GroupPipeline:
                     opts = dist.ProcessGroupNCCL.Options()
                     opts.config.min_ctas = 1
                     opts.config.max_ctas = 1
+                    opts.config.cga_cluster_size = 1
                 pg = dist.new_group(backend=backend, pg_options=opts) if opts is not None else dist.new_group(backend=backend)
             ctx = S.s.clone_context() if hasattr(S.s, "clone_context") else S.s
-            Sg = SlabSolver(ctx, S.n, S.b, S.rank, S.world, pg, device=self.device)
+            Sg = (solver_cls or SlabSolver)(ctx, S.n, S.b, S.rank, S.world, pg, device=self.device)
             Sg.R, Sg.j0, Sg.j1, Sg.rows, Sg.m_lo, Sg.m_hi = S.R, S.j0, S.j1, S.rows, S.m_lo, S.m_hi
+            Sg.mail = self.mails[g] if self.mails else None
             stream = torch.cuda.Stream(device=self.device) if (self.cuda and streams) else None
             self.members.append((Sg, pg, stream))
 
     def close(self):
+        if self.mails:
+            torch.cuda.synchronize()
+            dist.barrier()                                   # nobody writes into a mailbox any more
+            for m in self.mails:
+                m.close()
+            self.mails = []
         for Sg, pg, _ in self.members:
             if Sg.s is not self.S.s and hasattr(Sg.s, "close"):
                 Sg.s.close()
@@ -310,10 +474,8 @@ class GroupPipeline:
         assert len(rhs_groups) == self.G
         results, errors = [None] * self.G, [None] * self.G
         start = torch.cuda.Event() if self.cuda else None
-        if start is not None:
-            start.record()                                   # the groups start after what the caller has enqueued
 
-        def work(g):
+        def work(g, out, kwg):
             Sg, pg, stream = self.members[g]
             try:
                 with (torch.cuda.device(self.device) if self.cuda else contextlib.nullcontext()):
@@ -321,17 +483,36 @@ class GroupPipeline:
                         if stream is not None:
                             stream.wait_event(start)
                         vec = make_vec(rhs_groups[g][0].numel(), pg)
-                        results[g] = gmres_batch(lambda x, o: Sg.matvec(x, o), lambda reqs: Sg.precond_apply_batch(reqs, diag=diag),
-                                                 rhs_groups[g], vec=vec, matvec_batch=lambda reqs: Sg.matvec_batch(reqs), **kw)
+                        out[g] = gmres_batch(lambda x, o: Sg.matvec(x, o), lambda reqs: Sg.precond_apply_batch(reqs, diag=diag),
+                                             rhs_groups[g], vec=vec, matvec_batch=lambda reqs: Sg.matvec_batch(reqs), **kwg)
                         if stream is not None:
                             stream.synchronize()
-            except BaseException as e:                       # noqa: B902 - reported by the caller's thread
+            except BaseException as e:                       # noqa: B902 - re-raised by the caller's thread
+                import traceback
+                traceback.print_exc()                        # at once: the other groups/ranks may now wait for this one for ever
                 errors[g] = e
+
+        if not self.primed:
+            # Every group runs two iterations ALONE first, one group after the other on all ranks.  With lazy module loading
+            # (the CUDA 12 default) the first launch of a kernel may synchronise the whole context; once streams of this
+            # process wait for other GPUs that is a deadlock (measured: rank 1 blocked inside its first launch of the collect
+            # kernel behind the pending wait of another group, rank 0 likewise).  The pass also connects the communicator of
+            # every group and lets the contexts and the caching allocator of every stream make their allocations.
+            if start is not None:
+                start.record()
+            prime = dict(kw, rtol=0.0, atol=0.0, maxiter=2, callback=None)
+            for g in range(self.G):
+                work(g, [None] * self.G, prime)
+                if errors[g] is not None:
+                    raise errors[g]
+            self.primed = True
+        if start is not None:
+            start.record()                                   # the groups start after what the caller has enqueued
 
         old = sys.getswitchinterval()
         sys.setswitchinterval(1e-4)                          # a thread whose result has arrived should not wait 5 ms for the GIL
         try:
-            threads = [threading.Thread(target=work, args=(g,), name=f"hp-group-{g}") for g in range(self.G)]
+            threads = [threading.Thread(target=work, args=(g, results, kw), name=f"hp-group-{g}") for g in range(self.G)]
             for t in threads:
                 t.start()
             for t in threads:

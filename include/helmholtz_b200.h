@@ -157,6 +157,26 @@ int hp_mgs_step(int64_t n, const double* hcoef_dev, const double* v_dev, double*
 int hp_combine(int64_t n, int k, const double* V_dev, int64_t ldv, const double* y_host, double* x_dev,
                void* stream);
 
+/* ---- peer mailboxes (slab decomposition, helmholtz_preconditioner_b200/slab.py) --------------------------------------
+ * The reference runs algo2_4 (code.py:356-385) in one process; with the grid rows cut into slabs the row handed from
+ * strip m to strip m+1 (code.py:368-370, forward; 378-380, backward) crosses from one GPU to the next.  A mailbox is a
+ * block of device memory [256 bytes of uint32 flags | staging rows] that the neighbouring processes map (CUDA IPC): the
+ * sender stores the rows and then a sequence number, the receiver's stream waits for the number without holding an SM
+ * (cuStreamWaitValue32).  handle64: the 64 bytes of the cudaIpcMemHandle_t, to be passed to the other process. */
+int hp_mailbox_create(int64_t bytes, void** ptr_dev, unsigned char* handle64);
+int hp_mailbox_open(const unsigned char* handle64, void** ptr_dev);
+int hp_mailbox_close(void* ptr_dev);
+int hp_mailbox_free(void* ptr_dev);
+/* the stream waits until *(uint32*)flag_dev >= value */
+int hp_stream_wait_geq(const void* flag_dev, unsigned int value, void* stream);
+/* R <= 8 rows of n complex numbers: src_rows[r] -> staging_peer + r*n (complex), then *(uint32*)flag_peer = value */
+int hp_handover_rows(int R, const double* const* src_rows, double* staging_peer, int64_t n, void* flag_peer,
+                     unsigned int value, void* stream);
+/* staging + r*n -> dst_rows[r] on this device (after hp_stream_wait_geq on the flag that guards the staging area) */
+int hp_collect_rows(int R, const double* staging, double* const* dst_rows, int64_t n, void* stream);
+/* *(uint32*)flags_peer[i] = value for count <= 8 flags */
+int hp_signal_flags(int count, void* const* flags_peer, unsigned int value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
