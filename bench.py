@@ -55,6 +55,10 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tts", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="N > 1: skip slab_parity and the single-right-hand-side BASELINE configs")
+    ap.add_argument("--no-baseline-configs", action="store_true", help="N > 1: keep slab_parity, skip the single-right-hand-side BASELINE configs")
+    ap.add_argument("--parity-only", action="store_true", help="N > 1: run slab_parity, print it and stop")
+    ap.add_argument("--hang-dump", type=int, default=0, help="developer: after this many seconds write the Python stacks of all threads "
+                    "to gpurun_out/hang_rank<r>.txt and exit")
     ap.add_argument("--mp-schedule", default="lockstep", choices=["async", "lockstep"],
                     help="N > 1, pipelined mode: groups of right-hand sides as independent pipelines (slab.GroupPipeline) or all in lock step")
     ap.add_argument("--mp-mode", default="pipelined", choices=["pipelined", "weak"],
@@ -644,6 +648,10 @@ def run_b200_slabs(args):
     from helmholtz_preconditioner_b200.slab import distributed_gmres_setup
     from helmholtz_preconditioner_b200.gmres import CommStats, DeviceVectors, gmres_batch
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    if args.hang_dump:
+        import faulthandler
+        os.makedirs("gpurun_out", exist_ok=True)
+        faulthandler.dump_traceback_later(args.hang_dump, exit=True, file=open(f"gpurun_out/hang_rank{rank}.txt", "w"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     dist.init_process_group("nccl", device_id=dev)
@@ -658,6 +666,11 @@ def run_b200_slabs(args):
                 print(json.dumps({"metric": METRIC, "error": "slab_parity failed", "slab_parity": parity, "n_gpus": world}))
             dist.destroy_process_group()
             sys.exit(3)
+        if args.parity_only:
+            if rank == 0:
+                print(json.dumps({"slab_parity": parity}))
+            dist.destroy_process_group()
+            return
     out = None
     if args.mp_mode == "pipelined":
         w = workload(args, world)
@@ -751,7 +764,7 @@ def run_b200_slabs(args):
                             "multi-GPU); baseline_configs holds BASELINE.json's single-right-hand-side cases"),
                    "residual_last": hist_last}
     extras = {}
-    if not args.no_extras or args.mp_mode == "weak":
+    if (not args.no_extras and not args.no_baseline_configs) or args.mp_mode == "weak":
         nw = int(round(4096 * np.sqrt(world)))
         extras["weak_4096sq_per_gpu"] = slab_single_rhs(torch, dist, hp, args, nw, rank, world, dev)
         if world >= 4:

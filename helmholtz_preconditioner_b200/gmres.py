@@ -58,6 +58,7 @@ class DeviceVectors:
         self.nloc, self.device, self.group = nloc, torch.device(device), group
         self.scal = torch.zeros(max(64, restart + 3), dtype=torch.complex128, device=device)
         self.scalb = None                                    # scalars of a batch of systems, [restart + 3][R]
+        self._pin = None                                     # pinned host buffer of _host()
 
     def reserve(self, restart):
         """hp_mgs writes restart + 2 scalars (coefficients, norm after, norm before)"""
@@ -69,6 +70,20 @@ class DeviceVectors:
             self.scalb = torch.zeros((max(rows, self.scal.numel()), R), dtype=torch.complex128, device=self.device)
         return self.scalb
 
+    def _host(self, t):
+        """device scalars -> numpy, through a pinned buffer and a wait on the current stream only.  A copy to pageable
+        memory (.cpu(), .item()) returns when the copy is done and holds a lock of the driver until then: with several
+        host threads on one device (slab.GroupPipeline) a thread that waits that way for another GPU keeps the other
+        threads from launching the work that GPU is waiting for (measured at N = 2)."""
+        t = t.contiguous()
+        m = t.numel()
+        if self._pin is None or self._pin.numel() < m:
+            self._pin = torch.empty(max(m, 1024), dtype=torch.complex128).pin_memory()
+        h = self._pin[:m]
+        h.copy_(t.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h.numpy().reshape(t.shape).copy()
+
     def _all_reduce(self, t):
         import torch.distributed as dist
         CommStats.calls += 1
@@ -77,10 +92,10 @@ class DeviceVectors:
     def norm(self, x):
         if self.group is None:
             _lib.check(self.lib.hp_nrm2(self.nloc, _ptr(x), _ptr(self.scal), _stream()), "hp_nrm2")
-            return float(self.scal[0].real.item())
+            return float(self._host(self.scal[:1])[0].real)
         _lib.check(self.lib.hp_dotc(self.nloc, _ptr(x), _ptr(x), _ptr(self.scal), _stream()), "hp_dotc")
         self._all_reduce(self.scal[:1])
-        return math.sqrt(float(self.scal[0].real.item()))
+        return math.sqrt(float(self._host(self.scal[:1])[0].real))
 
     def norm_batch(self, xs):
         """norms of several vectors with one all-reduce and one copy to the host"""
@@ -93,7 +108,7 @@ class DeviceVectors:
                 _lib.check(self.lib.hp_dotc(self.nloc, _ptr(x), _ptr(x), _ptr(sc[i:]), _stream()), "hp_dotc")
         if self.group is not None:
             self._all_reduce(sc[:R])
-        v = sc[:R].cpu().numpy().real
+        v = self._host(sc[:R]).real
         return [float(t) for t in (v if self.group is None else np.sqrt(v))]
 
     def scale_copy(self, a, x, y):
@@ -119,13 +134,13 @@ class DeviceVectors:
             if R == 1:
                 V, _, w = items[0]
                 _lib.check(self.lib.hp_mgs(self.nloc, k, _ptr(V), V.stride(0), _ptr(w), _ptr(self.scal), _stream()), "hp_mgs")
-                h = self.scal[:k + 2].cpu().numpy()
+                h = self._host(self.scal[:k + 2])
                 return [(h[:k].copy(), float(h[k].real), float(h[k + 1].real))]
             sc = self._batch_scal(k + 2, R)                  # system i uses column i ... stored row-wise per system below
             flat = sc.view(-1)
             for i, (V, _, w) in enumerate(items):           # hp_mgs writes k + 2 consecutive scalars per system
                 _lib.check(self.lib.hp_mgs(self.nloc, k, _ptr(V), V.stride(0), _ptr(w), _ptr(flat[i * (k + 2):]), _stream()), "hp_mgs")
-            h = flat[:R * (k + 2)].cpu().numpy().reshape(R, k + 2)
+            h = self._host(flat[:R * (k + 2)]).reshape(R, k + 2)
             return [(h[i, :k].copy(), float(h[i, k].real), float(h[i, k + 1].real)) for i in range(R)]
         lib, n = self.lib, self.nloc
         sc = self._batch_scal(k + 2, R)                      # sc[j][i]: coefficient j of system i; rows k, k+1: |w|^2 after, before
@@ -142,7 +157,7 @@ class DeviceVectors:
             for i, (V, _, w) in enumerate(items):
                 _lib.check(lib.hp_dotc(n, _ptr(w), _ptr(w), _ptr(sc[0, i:]), _stream()), "hp_dotc")
         self._all_reduce(sc[k:k + 2, :R].reshape(-1) if sc.shape[1] == R else sc[k:k + 2, :R].contiguous())
-        h = sc[:k + 2, :R].cpu().numpy()
+        h = self._host(sc[:k + 2, :R])
         return [(h[:k, i].copy(), math.sqrt(float(h[k, i].real)), math.sqrt(float(h[k + 1, i].real))) for i in range(R)]
 
     def combine(self, V, y, x):
