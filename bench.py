@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--parity-only", action="store_true", help="N > 1: run slab_parity, print it and stop")
     ap.add_argument("--hang-dump", type=int, default=0, help="developer: after this many seconds write the Python stacks of all threads "
                     "to gpurun_out/hang_rank<r>.txt and exit")
-    ap.add_argument("--mp-schedule", default="lockstep", choices=["async", "lockstep"],
+    ap.add_argument("--mp-schedule", default="async", choices=["async", "lockstep"],
                     help="N > 1, pipelined mode: groups of right-hand sides as independent pipelines (slab.GroupPipeline) or all in lock step")
     ap.add_argument("--mp-mode", default="pipelined", choices=["pipelined", "weak"],
                     help="N > 1: 'pipelined' (default) = the 4096^2 problem slab-decomposed, --rhs right-hand sides per GPU sent through "
@@ -693,11 +693,12 @@ def run_b200_slabs(args):
             from helmholtz_preconditioner_b200.slab import GroupPipeline
             pipe = GroupPipeline(S, world)                        # one group of args.rhs right-hand sides per GPU
 
-        def iterations(k, rhs):
+        def iterations(k, rhs, host_out=None):
             if pipe is None:
                 return gmres_batch(mv, psb, rhs, vec=vec, matvec_batch=mvb, rtol=0.0, atol=0.0, restart=20, maxiter=k, nglobal=n * n)
-            res = pipe.gmres([rhs[g * args.rhs:(g + 1) * args.rhs] for g in range(world)],
-                             lambda nloc, pg: DeviceVectors(nloc, dev, group=pg), rtol=0.0, atol=0.0, restart=20, maxiter=k, nglobal=n * n)
+            cut = lambda xs: [xs[g * args.rhs:(g + 1) * args.rhs] for g in range(world)]      # noqa: E731
+            res = pipe.gmres(cut(rhs), lambda nloc, pg: DeviceVectors(nloc, dev, group=pg), rtol=0.0, atol=0.0, restart=20, maxiter=k,
+                             nglobal=n * n, host_out=None if host_out is None else cut(host_out))
             return [x for grp in res for x in grp]
 
         iterations(args.warmup, fs)
@@ -720,10 +721,14 @@ def run_b200_slabs(args):
         u_hosts = [torch.empty(fs[0].numel(), dtype=torch.complex128).pin_memory() for _ in range(R)]
         torch.cuda.synchronize(); dist.barrier()
         e0.record()
-        fs2 = [fh.to(dev, non_blocking=True) for fh in f_hosts]
-        res2 = iterations(args.steps, fs2)
-        for uh, (u2, _, _) in zip(u_hosts, res2):
-            uh.copy_(u2, non_blocking=True)
+        if pipe is None:
+            fs2 = [fh.to(dev, non_blocking=True) for fh in f_hosts]
+            res2 = iterations(args.steps, fs2)
+            for uh, (u2, _, _) in zip(u_hosts, res2):
+                uh.copy_(u2, non_blocking=True)
+        else:                                                # every group moves its own right-hand sides and solutions
+            fs2 = None
+            res2 = iterations(args.steps, f_hosts, host_out=u_hosts)
         e1.record()
         torch.cuda.synchronize(); dist.barrier()
         t_e2e = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)

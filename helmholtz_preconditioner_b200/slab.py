@@ -464,9 +464,12 @@ class GroupPipeline:
     def sweep_status(self):
         return max([int(Sg.s.sweep_status()) for Sg, _, _ in self.members if hasattr(Sg.s, "sweep_status")] + [0])
 
-    def gmres(self, rhs_groups, make_vec, *, diag="reference", **kw):
+    def gmres(self, rhs_groups, make_vec, *, diag="reference", host_out=None, **kw):
         """rhs_groups[g]: list of local right-hand side slabs of group g; make_vec(nloc, process_group) -> the vector
-        kernels of a group (gmres.DeviceVectors on a GPU).  Returns [[(x, info, hist), ...] per group]."""
+        kernels of a group (gmres.DeviceVectors on a GPU).  Returns [[(x, info, hist), ...] per group].
+        Right-hand sides given as (pinned) host tensors are copied to the device on the group's own stream, and with
+        host_out[g] = [pinned host tensor per system] the solutions go back the same way: the transfers of one group
+        overlap the sweeps of the others."""
         import contextlib
         import sys
         import threading
@@ -483,8 +486,12 @@ class GroupPipeline:
                         if stream is not None:
                             stream.wait_event(start)
                         vec = make_vec(rhs_groups[g][0].numel(), pg)
+                        rhs = [t.to(self.device, non_blocking=True) if (self.cuda and not t.is_cuda) else t for t in rhs_groups[g]]
                         out[g] = gmres_batch(lambda x, o: Sg.matvec(x, o), lambda reqs: Sg.precond_apply_batch(reqs, diag=diag),
-                                             rhs_groups[g], vec=vec, matvec_batch=lambda reqs: Sg.matvec_batch(reqs), **kwg)
+                                             rhs, vec=vec, matvec_batch=lambda reqs: Sg.matvec_batch(reqs), **kwg)
+                        if host_out is not None and out is results:
+                            for uh, (x, _, _) in zip(host_out[g], out[g]):
+                                uh.copy_(x, non_blocking=True)
                         if stream is not None:
                             stream.synchronize()
             except BaseException as e:                       # noqa: B902 - re-raised by the caller's thread
