@@ -23,6 +23,7 @@ SIGNATURES = {
     "hp_create": (_i, [C.POINTER(_vp), _i, _i, _d, _d, _d, _vp, _i, _vp]),
     "hp_destroy": (_i, [_vp]),
     "hp_context_clone": (_i, [_vp, C.POINTER(_vp), _vp]),
+    "hp_cgs_pass": (_i, [_i, _i64, _i, C.POINTER(_vp), _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i, _vp]),
     "hp_mailbox_create": (_i, [_i64, C.POINTER(_vp), _vp]),
     "hp_mailbox_open": (_i, [_vp, C.POINTER(_vp)]),
     "hp_mailbox_close": (_i, [_vp]),

@@ -53,9 +53,16 @@ class CommStats:
 class DeviceVectors:
     """Krylov vector kernels on (a slab of) the field; reductions are summed over `group` if given."""
 
-    def __init__(self, nloc, device, group=None, restart=20):
+    def __init__(self, nloc, device, group=None, restart=20, orth=None):
+        """orth: orthogonalisation of DISTRIBUTED vectors: "mgs" = modified Gram-Schmidt as scipy does it (k + 2 all-reduces
+        per Arnoldi column), "cgs2" = classical Gram-Schmidt applied twice (csrc/hp_cgs.cu: 3 all-reduces per column, the
+        Hessenberg entries agree with MGS to rounding).  Default: HP_ORTH or "cgs2".  Vectors on one device always use the
+        fused MGS kernels."""
+        import os
         self.lib = _lib.require_device()
         self.nloc, self.device, self.group = nloc, torch.device(device), group
+        self.orth = orth or os.environ.get("HP_ORTH", "cgs2")
+        self.cgs = None                                      # coefficient block of the cgs2 passes, [3][R][k + 1]
         self.scal = torch.zeros(max(64, restart + 3), dtype=torch.complex128, device=device)
         self.scalb = None                                    # scalars of a batch of systems, [restart + 3][R]
         self._pin = None                                     # pinned host buffer of _host()
@@ -143,6 +150,8 @@ class DeviceVectors:
             h = self._host(flat[:R * (k + 2)]).reshape(R, k + 2)
             return [(h[i, :k].copy(), float(h[i, k].real), float(h[i, k + 1].real)) for i in range(R)]
         lib, n = self.lib, self.nloc
+        if self.orth == "cgs2" and k <= 20:
+            return self._cgs2_batch(items)
         sc = self._batch_scal(k + 2, R)                      # sc[j][i]: coefficient j of system i; rows k, k+1: |w|^2 after, before
         for i, (V, _, w) in enumerate(items):
             _lib.check(lib.hp_dotc(n, _ptr(w), _ptr(w), _ptr(sc[k + 1, i:]), _stream()), "hp_dotc")
@@ -159,6 +168,27 @@ class DeviceVectors:
         self._all_reduce(sc[k:k + 2, :R].reshape(-1) if sc.shape[1] == R else sc[k:k + 2, :R].contiguous())
         h = self._host(sc[:k + 2, :R])
         return [(h[:k, i].copy(), math.sqrt(float(h[k, i].real)), math.sqrt(float(h[k + 1, i].real))) for i in range(R)]
+
+    def _cgs2_batch(self, items):
+        """mgs_batch for distributed vectors with classical Gram-Schmidt applied twice: per pass one launch per 8 systems
+        and ONE all-reduce of (k + 1) numbers per system for all of them"""
+        import ctypes as C
+        k, R = items[0][1], len(items)
+        m = k + 1                                            # pass p, system i: D[p, i * m : (i + 1) * m] = k coefficients, |w|^2
+        if self.cgs is None or self.cgs.shape[1] < R * 21:
+            self.cgs = torch.zeros((3, max(R, 8) * 21), dtype=torch.complex128, device=self.device)
+        D = self.cgs
+        arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])                        # noqa: E731
+        ldv = items[0][0].stride(0)
+        for p, (upd, dots) in enumerate(((0, 1), (1, 1), (1, 0))):
+            for i0 in range(0, R, 8):
+                idx = range(i0, min(R, i0 + 8))
+                coef = arr([D[p - 1, i * m:] for i in idx]) if upd else None
+                _lib.check(self.lib.hp_cgs_pass(len(idx), self.nloc, k, arr([items[i][0] for i in idx]), ldv, arr([items[i][2] for i in idx]),
+                                                coef, arr([D[p, i * m:] for i in idx]), upd, dots, _stream()), "hp_cgs_pass")
+            self._all_reduce(D[p, :R * m])
+        h = self._host(D[:, :R * m]).reshape(3, R, m)
+        return [((h[0, i, :k] + h[1, i, :k]).copy(), math.sqrt(float(h[2, i, k].real)), math.sqrt(float(h[0, i, k].real))) for i in range(R)]
 
     def combine(self, V, y, x):
         """x += sum_j y[j] V[j]."""

@@ -157,6 +157,16 @@ int hp_mgs_step(int64_t n, const double* hcoef_dev, const double* v_dev, double*
 int hp_combine(int64_t n, int k, const double* V_dev, int64_t ldv, const double* y_host, double* x_dev,
                void* stream);
 
+/* Block Gram-Schmidt pass on slab-distributed vectors (csrc/hp_cgs.cu): the orthogonalisation loop of scipy's gmres
+ * (w -= (v_j . w) v_j for j < k; called from code.py:516) as classical Gram-Schmidt applied twice, three passes and three
+ * all-reduces per Arnoldi column instead of k + 2.  For R <= 8 systems of n local entries and k <= 20 basis vectors (rows of
+ * V_devs[r], leading dimension ldv complex numbers):
+ *   update != 0:  w_r <- w_r - sum_j coef_devs[r][j] v_j      (k complex coefficients in device memory)
+ *   dots   != 0:  out_devs[r][j] = v_j^H w_r for j < k, from the updated w_r
+ *   always:       out_devs[r][k] = sum |w_r|^2 from the updated w_r  */
+int hp_cgs_pass(int R, int64_t n, int k, const double* const* V_devs, int64_t ldv, double* const* w_devs,
+                const double* const* coef_devs, double* const* out_devs, int update, int dots, void* stream);
+
 /* ---- peer mailboxes (slab decomposition, helmholtz_preconditioner_b200/slab.py) --------------------------------------
  * The reference runs algo2_4 (code.py:356-385) in one process; with the grid rows cut into slabs the row handed from
  * strip m to strip m+1 (code.py:368-370, forward; 378-380, backward) crosses from one GPU to the next.  A mailbox is a

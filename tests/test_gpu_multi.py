@@ -108,3 +108,76 @@ def test_group_pipeline_one_gpu(hp, front):
             assert torch.equal(u, u0)
     s.check_status()
     s.close()
+
+
+@pytest.mark.parametrize("n,k,R", [(1000, 1, 1), (70001, 4, 3), (300000, 5, 8), (2097152, 13, 8), (123457, 20, 2), (5000, 0, 2)])
+def test_cgs_pass_kernels(hp, n, k, R):
+    """csrc/hp_cgs.cu: dots of w against k basis vectors + |w|^2, the block update, for R systems in one launch, against torch"""
+    import ctypes as C
+    from helmholtz_preconditioner_b200 import _lib
+    lib = _lib.require_device()
+    g = torch.Generator(device="cuda").manual_seed(n + k)
+    rnd = lambda *s: torch.randn(*s, dtype=torch.complex128, device="cuda", generator=g)      # noqa: E731
+    Vs = [rnd(21, n) for _ in range(R)]
+    ws = [rnd(n) for _ in range(R)]
+    w0 = [w.clone() for w in ws]
+    out = torch.zeros((2, R, 21), dtype=torch.complex128, device="cuda")
+    arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])                          # noqa: E731
+    st = torch.cuda.current_stream().cuda_stream
+    # pass A: dots and norm, w untouched
+    _lib.check(lib.hp_cgs_pass(R, n, k, arr(Vs), Vs[0].stride(0), arr(ws), None, arr([out[0, i] for i in range(R)]), 0, 1, st), "hp_cgs_pass")
+    for i in range(R):
+        assert torch.equal(ws[i], w0[i])
+        d = Vs[i][:k].conj() @ w0[i]
+        if k:
+            assert (torch.linalg.norm(out[0, i, :k] - d) / torch.linalg.norm(Vs[i][:k].abs() @ w0[i].abs())).item() < 1e-13
+        assert abs(out[0, i, k].real.item() - torch.linalg.norm(w0[i]).item() ** 2) < 1e-12 * out[0, i, k].real.item()
+    if k == 0:
+        return
+    # pass B: update with the coefficients of pass A, dots and norm of the updated vector; pass C: update only + norm
+    for upd_dots, slot in ((1, 1), (0, 1)):
+        before = [w.clone() for w in ws]
+        coef = out[0].clone() if upd_dots else out[1].clone()
+        _lib.check(lib.hp_cgs_pass(R, n, k, arr(Vs), Vs[0].stride(0), arr(ws), arr([coef[i] for i in range(R)]),
+                                   arr([out[slot, i] for i in range(R)]), 1, upd_dots, st), "hp_cgs_pass")
+        for i in range(R):
+            ref = before[i] - coef[i, :k] @ Vs[i][:k]
+            assert (torch.linalg.norm(ws[i] - ref) / torch.linalg.norm(ref)).item() < 1e-13
+            if upd_dots:
+                d = Vs[i][:k].conj() @ ref
+                assert (torch.linalg.norm(out[slot, i, :k] - d) / torch.linalg.norm(Vs[i][:k].abs() @ ref.abs())).item() < 1e-13      # scale of the sums
+            assert abs(out[slot, i, k].real.item() - torch.linalg.norm(ref).item() ** 2) < 1e-12 * out[slot, i, k].real.item()
+
+
+def test_cgs2_matches_mgs(hp):
+    """DeviceVectors on 'distributed' vectors (a process group of one rank): classical Gram-Schmidt twice against the
+    modified Gram-Schmidt path: same coefficients and the same orthogonalised vector to rounding"""
+    import os
+    import socket
+    import torch.distributed as dist
+    from helmholtz_preconditioner_b200.gmres import DeviceVectors
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        n, k, R = 200003, 9, 5
+        g = torch.Generator(device="cuda").manual_seed(3)
+        items = []
+        for _ in range(R):
+            Q, _r = torch.linalg.qr(torch.randn(n, k, dtype=torch.complex128, device="cuda", generator=g))
+            V = torch.zeros(21, n, dtype=torch.complex128, device="cuda")
+            V[:k] = Q.T
+            items.append((V, k, torch.randn(n, dtype=torch.complex128, device="cuda", generator=g)))
+        a = DeviceVectors(n, "cuda", group=dist.group.WORLD, orth="mgs")
+        b = DeviceVectors(n, "cuda", group=dist.group.WORLD, orth="cgs2")
+        ia = [(V, k, w.clone()) for V, k, w in items]
+        ib = [(V, k, w.clone()) for V, k, w in items]
+        ra, rb = a.mgs_batch(ia), b.mgs_batch(ib)
+        for (ha, na1, na0), (hb, nb1, nb0), (_, _, wa), (_, _, wb) in zip(ra, rb, ia, ib):
+            assert np.linalg.norm(ha - hb) / np.linalg.norm(ha) < 1e-13
+            assert abs(na1 - nb1) < 1e-13 * na1 and abs(na0 - nb0) < 1e-13 * na0
+            assert (torch.linalg.norm(wa - wb) / torch.linalg.norm(wa)).item() < 1e-13
+    finally:
+        dist.destroy_process_group()
