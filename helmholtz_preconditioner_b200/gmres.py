@@ -55,13 +55,15 @@ class DeviceVectors:
 
     def __init__(self, nloc, device, group=None, restart=20, orth=None):
         """orth: orthogonalisation of DISTRIBUTED vectors: "mgs" = modified Gram-Schmidt as scipy does it (k + 2 all-reduces
-        per Arnoldi column), "cgs2" = classical Gram-Schmidt applied twice (csrc/hp_cgs.cu: 3 all-reduces per column, the
-        Hessenberg entries agree with MGS to rounding).  Default: HP_ORTH or "cgs2".  Vectors on one device always use the
-        fused MGS kernels."""
+        per Arnoldi column, fused axpy + next dot passes), "cgs2" = classical Gram-Schmidt applied twice (csrc/hp_cgs.cu:
+        3 block passes and 3 all-reduces per column, the Hessenberg entries agree with MGS to 1e-13).  Default: HP_ORTH or
+        "mgs": measured in the group pipeline of bench.py, cgs2 is slower (N = 2: 128 vs 132 iters/s, N = 4: 250 vs 283) - the
+        register-heavy block passes run at lower occupancy than the fused MGS passes (98 % of HBM peak) and the saved
+        all-reduces do not pay for it.  Vectors on one device always use the fused MGS kernels."""
         import os
         self.lib = _lib.require_device()
         self.nloc, self.device, self.group = nloc, torch.device(device), group
-        self.orth = orth or os.environ.get("HP_ORTH", "cgs2")
+        self.orth = orth or os.environ.get("HP_ORTH", "mgs")
         self.cgs = None                                      # coefficient block of the cgs2 passes, [3][R][k + 1]
         self.scal = torch.zeros(max(64, restart + 3), dtype=torch.complex128, device=device)
         self.scalb = None                                    # scalars of a batch of systems, [restart + 3][R]
