@@ -648,10 +648,15 @@ def run_b200_slabs(args):
     from helmholtz_preconditioner_b200.slab import distributed_gmres_setup
     from helmholtz_preconditioner_b200.gmres import CommStats, DeviceVectors, gmres_batch
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    import faulthandler
     if args.hang_dump:
-        import faulthandler
         os.makedirs("gpurun_out", exist_ok=True)
         faulthandler.dump_traceback_later(args.hang_dump, exit=True, file=open(f"gpurun_out/hang_rank{rank}.txt", "w"))
+    else:
+        # watchdog: the ranks of a multi-GPU run wait for each other on the device; if that ever stops making progress the
+        # process must end (stacks of all threads on stderr, non-zero exit, torchrun takes the other ranks down) instead
+        # of holding the box until somebody else's limit
+        faulthandler.dump_traceback_later(1200, exit=True, file=sys.stderr)
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     dist.init_process_group("nccl", device_id=dev)
@@ -772,7 +777,9 @@ def run_b200_slabs(args):
     if (not args.no_extras and not args.no_baseline_configs) or args.mp_mode == "weak":
         nw = int(round(4096 * np.sqrt(world)))
         extras["weak_4096sq_per_gpu"] = slab_single_rhs(torch, dist, hp, args, nw, rank, world, dev)
-        if world >= 4:
+        if world >= 4 and nw == 8192:                   # N = 4: the weak case IS the 8192^2 problem
+            extras["strong_8192sq"] = dict(extras["weak_4096sq_per_gpu"], same_run_as="weak_4096sq_per_gpu")
+        elif world >= 4:
             extras["strong_8192sq"] = slab_single_rhs(torch, dist, hp, args, 8192, rank, world, dev)
         else:
             extras["strong_8192sq"] = {"n": 8192, "skipped": "the strip factors of 8192^2 (~320 GB) need at least 4 GPUs of 180 GB"}
