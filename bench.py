@@ -656,7 +656,7 @@ def run_b200_slabs(args):
         # watchdog: the ranks of a multi-GPU run wait for each other on the device; if that ever stops making progress the
         # process must end (stacks of all threads on stderr, non-zero exit, torchrun takes the other ranks down) instead
         # of holding the box until somebody else's limit
-        faulthandler.dump_traceback_later(1200, exit=True, file=sys.stderr)
+        faulthandler.dump_traceback_later(800, exit=True, file=sys.stderr)
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     dist.init_process_group("nccl", device_id=dev)
