@@ -774,15 +774,38 @@ def run_b200_slabs(args):
                             "multi-GPU); baseline_configs holds BASELINE.json's single-right-hand-side cases"),
                    "residual_last": hist_last}
     extras = {}
+    guard = None
+    if args.mp_mode == "pipelined":
+        # The single-right-hand-side BASELINE configurations are extras of the line: if they do not come back (a rank that
+        # fails alone leaves the others waiting in a collective), the headline that has been measured is printed without
+        # them and every rank ends with exit code 0.
+        def give_up():
+            if rank == 0 and out is not None:
+                out["baseline_configs"] = dict(extras, error="not finished after 300 s; the headline above was measured before")
+                out["slab_parity"] = parity
+                print(json.dumps(out), flush=True)
+            os._exit(0)
+        guard = threading.Timer(300.0, give_up)
+        guard.daemon = True
+        guard.start()
     if (not args.no_extras and not args.no_baseline_configs) or args.mp_mode == "weak":
         nw = int(round(4096 * np.sqrt(world)))
-        extras["weak_4096sq_per_gpu"] = slab_single_rhs(torch, dist, hp, args, nw, rank, world, dev)
+
+        def single(nn):
+            try:
+                return slab_single_rhs(torch, dist, hp, args, nn, rank, world, dev)
+            except Exception as e:                           # noqa: BLE001 - reported in the line; the same on every rank
+                return {"n": nn, "error": f"{type(e).__name__}: {e}"}
+
+        extras["weak_4096sq_per_gpu"] = single(nw)
         if world >= 4 and nw == 8192:                   # N = 4: the weak case IS the 8192^2 problem
             extras["strong_8192sq"] = dict(extras["weak_4096sq_per_gpu"], same_run_as="weak_4096sq_per_gpu")
         elif world >= 4:
-            extras["strong_8192sq"] = slab_single_rhs(torch, dist, hp, args, 8192, rank, world, dev)
+            extras["strong_8192sq"] = single(8192)
         else:
             extras["strong_8192sq"] = {"n": 8192, "skipped": "the strip factors of 8192^2 (~320 GB) need at least 4 GPUs of 180 GB"}
+    if guard is not None:
+        guard.cancel()
     if rank == 0:
         if out is None:                              # --mp-mode weak: the weak case is the line
             e = extras["weak_4096sq_per_gpu"]
