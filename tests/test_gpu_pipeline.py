@@ -25,7 +25,7 @@ def _free_port():
 def _worker(rank, world, port, n, b, ret):
     import faulthandler
     import sys
-    faulthandler.dump_traceback_later(150, exit=True, file=sys.stderr)     # a hang ends with the stacks of all threads
+    faulthandler.dump_traceback_later(300, exit=True, file=sys.stderr)     # a hang ends with the stacks of all threads
     os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")   # no context-wide synchronisation at the first launch of a kernel
     try:
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
