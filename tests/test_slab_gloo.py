@@ -291,3 +291,18 @@ def test_group_pipeline_matches_lock_step(world):
         for (u, info, hist), (u0, info0, hist0) in zip(ret[r]["pipe"], ret[r]["lock"]):
             assert info == info0 and len(hist) == len(hist0) and np.allclose(hist, hist0, rtol=1e-10)
             assert np.linalg.norm(u - u0) / np.linalg.norm(u0) < 1e-10
+
+
+def test_pipeline_model_sanity():
+    """tools/pipeline_model.py: one rank and one group is the plain sum of the parts; the asynchronous schedule is never
+    slower than lock step in the model; more groups per rank raise the utilisation"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pipeline_model", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "pipeline_model.py"))
+    pm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pm)
+    one = pm.simulate(1, 1, "lockstep", handover_ms=0.0, sync_ms=0.0)
+    assert abs(one - (2 * 31.7 * 1.1 + 19.2)) < 0.5
+    for N in (2, 4, 8):
+        a, l = pm.simulate(N, N, "async"), pm.simulate(N, N, "lockstep")
+        assert a <= l * 1.02
+        assert pm.simulate(N, 2 * N, "async") / 2 < a
