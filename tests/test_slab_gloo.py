@@ -268,8 +268,12 @@ def _group_worker(rank, world, port, n, b, ret):
     loc = [torch.from_numpy(np.ascontiguousarray(f[S.j0:S.j1].ravel().astype(np.complex128))) for f in fs]
     kw = dict(rtol=1e-3, restart=20, maxiter=9, nglobal=n * n)
     pipe = GroupPipeline(S, 3, device="cpu", backend="gloo")
-    res = pipe.gmres([loc[0:2], loc[2:4], loc[4:6]], lambda nloc, pg: NumpyVectors(pg), **kw)
+    outs = [[torch.zeros_like(x) for x in grp] for grp in (loc[0:2], loc[2:4], loc[4:6])]
+    res = pipe.gmres([loc[0:2], loc[2:4], loc[4:6]], lambda nloc, pg: NumpyVectors(pg), host_out=outs, **kw)
     pipe.close()
+    for grp, og in zip(res, outs):                           # the solutions also arrive in the buffers handed in
+        for (u, _, _), o in zip(grp, og):
+            assert torch.equal(u, o)
     vec = NumpyVectors()
     lock = gmres_batch(lambda x, o: S.matvec(x, o), lambda reqs: S.precond_apply_batch(reqs), loc, vec=vec,
                        matvec_batch=lambda reqs: S.matvec_batch(reqs), **kw)
